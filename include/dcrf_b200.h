@@ -1,0 +1,149 @@
+/*
+ * dcrf_b200.h -- C ABI of the B200-native DenseCRF mean-field engine (libdcrf_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of lyndonchan/wsss-analysis: the fully-connected
+ * DenseCRF that the reference reaches through the (un-vendored) `pydensecrf` Python class API.  Each
+ * entry point names the reference interface it replaces.  File:line citations are into
+ * /root/reference; "[EXT]" marks pydensecrf behaviour recalled from the public package, which is
+ * not present in the reference tree.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints and floats only; no torch / numpy types.
+ *   - every function returns 0 on success, a DCRF_E* code otherwise; dcrf_last_error() gives the
+ *     thread-local message of the last failure on the calling thread.
+ *   - a handle holds a BATCH of B >= 1 independent images that share the label count L.  A single
+ *     pydensecrf `DenseCRF2D(w, h, L)` object (03c_hsn/utilities.py:427) is a batch of one.
+ *   - pixel index p = y*W + x; per-image matrices are row-major (L, N_b) float32 exactly as the
+ *     Python callers hand them over (03c_hsn/utilities.py:431-432, 443); in a batch the per-image
+ *     blocks are laid back to back in image order ("concatenated").
+ *   - `on_device` = 0: the pointer is host memory (pageable or pinned); 1: device memory on the
+ *     handle's device.  All work is enqueued on the handle's stream; calls that return host data
+ *     synchronise that stream before returning, calls that only take device pointers do not.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with DCRF_ECUDA.
+ */
+#ifndef DCRF_B200_H
+#define DCRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dcrf_handle dcrf_t;
+
+/* error codes */
+enum {
+    DCRF_OK = 0,
+    DCRF_EINVAL = 1, /* bad argument (shape, enum, NULL)   -> Python ValueError */
+    DCRF_ECUDA = 2,  /* CUDA runtime failure / no device   -> Python RuntimeError */
+    DCRF_ESTATE = 3, /* call sequence error (e.g. inference before setUnaryEnergy) */
+    DCRF_ENOMEM = 4
+};
+
+/* [EXT] pydensecrf.densecrf enums; only DIAG_KERNEL + NORMALIZE_SYMMETRIC (the defaults) are
+ * exercised by the reference (03c_hsn/utilities.py:435,439-440). */
+enum { DCRF_CONST_KERNEL = 0, DCRF_DIAG_KERNEL = 1, DCRF_FULL_KERNEL = 2 };
+enum {
+    DCRF_NO_NORMALIZATION = 0,
+    DCRF_NORMALIZE_BEFORE = 1,
+    DCRF_NORMALIZE_AFTER = 2,
+    DCRF_NORMALIZE_SYMMETRIC = 3
+};
+/* [EXT] label compatibility: a number -> Potts, a 1-D array -> diagonal, a 2-D array -> matrix */
+enum { DCRF_COMPAT_POTTS = 0, DCRF_COMPAT_DIAGONAL = 1, DCRF_COMPAT_MATRIX = 2 };
+
+const char *dcrf_last_error(void);
+/* library / build identification, e.g. "dcrf_b200 0.1 sm_100a" */
+const char *dcrf_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t dcrf_launch_count(void);
+
+/* ---- construction --------------------------------------------------------------------------- */
+
+/* Replaces `dcrf.DenseCRF2D(w, h, nlabels)` (03c_hsn/utilities.py:427; width first).
+ * device < 0 = current device; stream = a cudaStream_t (NULL = the library creates its own). */
+int dcrf_create(int w, int h, int n_labels, int device, void *stream, dcrf_t **out);
+
+/* [EXT] `DenseCRF(nvar, nlabels)`: a model over n_vars variables without image geometry; only
+ * dcrf_add_pairwise_energy() is available on it. */
+int dcrf_create_nd(int n_vars, int n_labels, int device, void *stream, dcrf_t **out);
+
+/* Batch of n_images images with per-image sizes.  Replaces the serial per-image loops of the
+ * reference: `for iter_input_image in range(num_input_images)` (03c_hsn/utilities.py:424),
+ * `for i in range(batch_size)` (03a_sec-dsrg/SEC.py:274, DSRG.py:327). */
+int dcrf_create_batch(int n_images, const int *w, const int *h, int n_labels, int device,
+                      void *stream, dcrf_t **out);
+
+void dcrf_destroy(dcrf_t *h);
+/* block the calling thread until everything enqueued on the handle's stream has finished */
+int dcrf_synchronize(dcrf_t *h);
+
+/* ---- model set-up (every setter copies; the caller keeps ownership of its buffers) --------- */
+
+/* Replaces `d.setUnaryEnergy(U)` (03c_hsn/utilities.py:432).  U: concatenated (L, N_b) blocks. */
+int dcrf_set_unary(dcrf_t *h, const float *U, int on_device);
+
+/* Replaces `d.addPairwiseGaussian(sxy=(sx,sy), compat=...)` (03c_hsn/utilities.py:435).
+ * compat: 1 float (Potts), L floats (diagonal) or L*L floats row-major (matrix); HOST memory. */
+int dcrf_add_pairwise_gaussian(dcrf_t *h, float sx, float sy, int compat_kind, const float *compat,
+                               int kernel_type, int normalization_type);
+
+/* Replaces `d.addPairwiseBilateral(sxy, srgb, rgbim, compat)` (03c_hsn/utilities.py:439-440).
+ * rgb: concatenated (H_b, W_b, 3) uint8 images; read only during this call. */
+int dcrf_add_pairwise_bilateral(dcrf_t *h, float sx, float sy, float sr, float sg, float sb,
+                                const uint8_t *rgb, int on_device, int compat_kind,
+                                const float *compat, int kernel_type, int normalization_type);
+
+/* [EXT] `addPairwiseEnergy(features, compat, kernel, normalization)`: features row-major (d, N),
+ * 1 <= d <= 7.  Single-image / nd handles only. */
+int dcrf_add_pairwise_energy(dcrf_t *h, const float *features, int d, int on_device, int compat_kind,
+                             const float *compat, int kernel_type, int normalization_type);
+
+/* ---- inference -------------------------------------------------------------------------------- */
+
+/* Replaces `Q = d.inference(n)` + `np.array(Q)` (03c_hsn/utilities.py:442-443): runs n mean-field
+ * iterations from the unary and writes the marginals as concatenated (L, N_b) float32 blocks. */
+int dcrf_inference(dcrf_t *h, int n_iter, float *Q_out, int on_device);
+
+/* inference + per-pixel argmax over labels (first maximum wins, like np.argmax):
+ * replaces `np.argmax(np.array(Q).reshape(L,H,W), axis=0)` (03c_hsn/utilities.py:443-444,
+ * [EXT] crf_inference_label used by 03b_irn/step/cam_to_ir_label.py:35).  labels: sum(N_b) int32. */
+int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device);
+
+/* [EXT] startInference / stepInference / klDivergence.  The running Q lives inside the handle. */
+int dcrf_start_inference(dcrf_t *h);
+int dcrf_step_inference(dcrf_t *h);
+int dcrf_get_q(dcrf_t *h, float *Q_out, int on_device);
+int dcrf_set_q(dcrf_t *h, const float *Q_in, int on_device);
+int dcrf_kl_divergence(dcrf_t *h, double *kl_out); /* of the running Q; batch-of-one only */
+
+/* ---- introspection (bit-exact lattice tests) ------------------------- */
+
+int dcrf_num_pairwise(dcrf_t *h, int *n_out);
+/* dimension d, total vertex count M over the batch, and (optional) per-image vertex counts */
+int dcrf_lattice_info(dcrf_t *h, int kernel, int *d_out, int64_t *M_out, int64_t *M_per_image);
+/* Host buffers (any may be NULL), all in the reference numbering of Appendix A.3 (vertex id = rank
+ * of the key's first occurrence in pixel-major / remainder-minor scan order), for image `image`:
+ *   keys (M_b, d) int16; offsets (N_b, d+1) int32; bary (N_b, d+1) float32;
+ *   neighbours (d+1, M_b, 2) int32 with -1 = absent; norm (N_b) float32. */
+int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t *offsets,
+                        float *bary, int32_t *neighbours, float *norm);
+/* one application of pairwise kernel `kernel`'s lattice filter (splat, blur, slice; no norm, no
+ * compat) to host values (L, N) -> (L, N); batch-of-one only.  Test hook. */
+int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int value_size);
+
+/* ---- evaluation reduction (the integer collective behind mIoU) --------------------------------- */
+
+/* Replaces chainercv `calc_semantic_segmentation_confusion` as called at
+ * 03b_irn/step/eval_sem_seg.py:41 and the per-class loops of 03a_sec-dsrg/model.py:698-719:
+ * conf is (C+1, C) int64 DEVICE memory, row = GT class, column = predicted class, row C collects
+ * pixels whose GT is outside [0, C) (ignored).  Accumulates (does not clear).  gt/pred: device int32.
+ * Predictions outside [0, C) are counted into *n_bad_pred (device int64, may be NULL). */
+int dcrf_confusion_accumulate(const int32_t *gt, const int32_t *pred, int64_t n, int n_classes,
+                              int64_t *conf, int64_t *n_bad_pred, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCRF_B200_H */

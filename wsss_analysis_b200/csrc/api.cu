@@ -1,0 +1,588 @@
+// api.cu -- the extern "C" boundary (include/dcrf_b200.h) and the host-side orchestration of the
+// mean-field loop.  One handle = a batch of independent images sharing L; all kernels run over the
+// concatenated pixel / vertex arrays of the batch on the handle's stream.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+
+namespace dcrf {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string t_error;
+void set_error(const std::string &msg) { t_error = msg; }
+
+struct Pairwise {
+    Lattice lat;
+    DevBuf<float> norm;    // [Ntot]; empty for NO_NORMALIZATION
+    DevBuf<float> compat;  // diagonal: [Lp]; matrix: [Lp*Lp] zero padded
+    DevBuf<float> valA, valB;  // lattice value ping-pong, [M * Lp]
+    int ntype = DCRF_NORMALIZE_SYMMETRIC, ktype = DCRF_DIAG_KERNEL;
+    int compat_kind = DCRF_COMPAT_POTTS;
+    float potts_w = 0.f;
+};
+
+}  // namespace dcrf
+
+using namespace dcrf;
+
+struct dcrf_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int L = 0, Lp = 0;
+    bool has_geom = false;  // 2-D image geometry available (Gaussian / bilateral features)
+    BatchGeom geom;
+    DevBuf<int> d_w, d_h, d_pix_start;
+    DevBuf<float> unary, Q;
+    bool unary_set = false, q_valid = false;
+    std::vector<std::unique_ptr<Pairwise>> pw;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) DCRF_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return DCRF_OK;
+    } catch (const Error &e) {
+        set_error(e.msg);
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        set_error("out of host memory");
+        return DCRF_ENOMEM;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return DCRF_EINVAL;
+    }
+}
+
+int64_t total_ln(const dcrf_handle *h) { return h->geom.Ntot * (int64_t)h->L; }
+
+void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, int device, void *stream,
+                   dcrf_t **out) {
+    DCRF_REQUIRE(out != nullptr, DCRF_EINVAL, "out handle pointer is NULL");
+    DCRF_REQUIRE(B >= 1, DCRF_EINVAL, "n_images must be >= 1");
+    DCRF_REQUIRE(L >= 0, DCRF_EINVAL, "n_labels must be >= 0");
+    DCRF_REQUIRE(L <= 128, DCRF_EINVAL, "n_labels > 128 is not supported");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw Error{DCRF_ECUDA, std::string("no CUDA device: dcrf_b200 has no CPU fallback (") +
+                                    cudaGetErrorString(ce) + ")"};
+    if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
+    DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
+    std::unique_ptr<dcrf_handle> h(new dcrf_handle());
+    h->device = device;
+    DeviceGuard guard(device);
+    static std::atomic<uint64_t> pool_configured{0};
+    if (!(pool_configured.load() & (1ull << device))) {
+        cudaMemPool_t pool;
+        DCRF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_configured.fetch_or(1ull << device);
+    }
+    if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        DCRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    h->L = L;
+    h->Lp = ((L + 3) / 4) * 4;
+    h->has_geom = has_geom;
+    BatchGeom &g = h->geom;
+    g.B = B;
+    g.w.resize(B);
+    g.h.resize(B);
+    g.pix_start.assign(B + 1, 0);
+    std::vector<int> ps32(B + 1, 0);
+    for (int b = 0; b < B; b++) {
+        DCRF_REQUIRE(w[b] >= 1 && hgt[b] >= 1, DCRF_EINVAL, "image width/height must be >= 1");
+        g.w[b] = w[b];
+        g.h[b] = hgt[b];
+        g.pix_start[b + 1] = g.pix_start[b] + (int64_t)w[b] * hgt[b];
+        DCRF_REQUIRE(g.pix_start[b + 1] < (int64_t)1 << 30, DCRF_EINVAL, "batch has too many pixels");
+        ps32[b + 1] = (int)g.pix_start[b + 1];
+    }
+    g.Ntot = g.pix_start[B];
+    h->d_w.alloc(B, h->stream);
+    h->d_h.alloc(B, h->stream);
+    h->d_pix_start.alloc(B + 1, h->stream);
+    DCRF_CUDA(cudaMemcpyAsync(h->d_w.p, g.w.data(), sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    DCRF_CUDA(cudaMemcpyAsync(h->d_h.p, g.h.data(), sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    DCRF_CUDA(cudaMemcpyAsync(h->d_pix_start.p, ps32.data(), sizeof(int) * (B + 1),
+                              cudaMemcpyHostToDevice, h->stream));
+    DCRF_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope
+    g.d_w = h->d_w.p;
+    g.d_h = h->d_h.p;
+    g.d_pix_start = h->d_pix_start.p;
+    if (h->Lp > 0) {
+        h->unary.alloc((size_t)g.Ntot * h->Lp, h->stream);
+        h->Q.alloc((size_t)g.Ntot * h->Lp, h->stream);
+        DCRF_CUDA(cudaMemsetAsync(h->unary.p, 0, sizeof(float) * g.Ntot * h->Lp, h->stream));
+    }
+    *out = h.release();
+}
+
+// bring `count` elements to the device if they are on the host; returns the device pointer
+template <typename T>
+const T *to_device(dcrf_handle *h, const T *src, size_t count, int on_device, DevBuf<T> &stage) {
+    if (on_device) return src;
+    stage.alloc(count, h->stream);
+    DCRF_CUDA(cudaMemcpyAsync(stage.p, src, sizeof(T) * count, cudaMemcpyHostToDevice, h->stream));
+    return stage.p;
+}
+
+// splat + (d+1) blurs of pairwise k applied to `in` (pixel-major Lp); returns the blurred buffer
+const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int Lp, bool pre_norm,
+                               bool seq, float *bufA, float *bufB) {
+    launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, h->stream);
+    float *cur = bufA, *nxt = bufB;
+    for (int j = 0; j <= p.lat.d; j++) {
+        launch_blur(p.lat, j, cur, nxt, Lp, seq, h->stream);
+        std::swap(cur, nxt);
+    }
+    return cur;
+}
+
+void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const float *compat, int ktype,
+                  int ntype) {
+    DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+    DCRF_REQUIRE((int)h->pw.size() < kMaxPairwise, DCRF_EINVAL, "too many pairwise terms (max 4)");
+    DCRF_REQUIRE(ktype >= DCRF_CONST_KERNEL && ktype <= DCRF_FULL_KERNEL, DCRF_EINVAL, "bad kernel type");
+    DCRF_REQUIRE(ntype >= DCRF_NO_NORMALIZATION && ntype <= DCRF_NORMALIZE_SYMMETRIC, DCRF_EINVAL,
+                 "bad normalization type");
+    DCRF_REQUIRE(compat_kind >= DCRF_COMPAT_POTTS && compat_kind <= DCRF_COMPAT_MATRIX, DCRF_EINVAL,
+                 "bad compatibility kind");
+    DCRF_REQUIRE(compat != nullptr, DCRF_EINVAL, "compat is NULL");
+    cudaStream_t s = h->stream;
+    const int L = h->L, Lp = h->Lp;
+    const int64_t Ntot = h->geom.Ntot;
+    std::unique_ptr<Pairwise> p(new Pairwise());
+    p->ktype = ktype;  // CONST / DIAG / FULL are all the identity feature map at default parameters
+    p->ntype = ntype;
+    p->compat_kind = compat_kind;
+    if (compat_kind == DCRF_COMPAT_POTTS) {
+        p->potts_w = compat[0];
+    } else if (compat_kind == DCRF_COMPAT_DIAGONAL) {
+        std::vector<float> c(Lp, 0.f);
+        for (int l = 0; l < L; l++) c[l] = compat[l];
+        p->compat.alloc(Lp, s);
+        DCRF_CUDA(cudaMemcpyAsync(p->compat.p, c.data(), sizeof(float) * Lp, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(cudaStreamSynchronize(s));
+    } else {
+        // [EXT] MatrixCompatibility stores 0.5 * (m + m^T)
+        std::vector<float> c((size_t)Lp * Lp, 0.f);
+        for (int a = 0; a < L; a++)
+            for (int b = 0; b < L; b++) c[(size_t)a * Lp + b] = 0.5f * (compat[a * L + b] + compat[b * L + a]);
+        p->compat.alloc((size_t)Lp * Lp, s);
+        DCRF_CUDA(cudaMemcpyAsync(p->compat.p, c.data(), sizeof(float) * Lp * Lp, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(cudaStreamSynchronize(s));
+    }
+    build_lattice(h->geom, fs, p->lat, s);
+    // A.5: norm = filter(ones) through the value_size = 1 path
+    if (ntype != DCRF_NO_NORMALIZATION) {
+        DevBuf<float> ones, a, b, sliced;
+        ones.alloc((size_t)Ntot * 4, s);
+        a.alloc((size_t)p->lat.M * 4, s);
+        b.alloc((size_t)p->lat.M * 4, s);
+        sliced.alloc((size_t)Ntot * 4, s);
+        launch_fill_ones_col0(ones.p, Ntot, 4, s);
+        const float *blurred = filter_to_lattice(h, *p, ones.p, 4, false, true, a.p, b.p);
+        launch_slice_plain(p->lat, blurred, sliced.p, Ntot, 4, true, s);
+        p->norm.alloc(Ntot, s);
+        launch_norm_finalize(sliced.p, 4, p->norm.p, Ntot, ntype, s);
+    }
+    p->valA.alloc((size_t)p->lat.M * Lp, s);
+    p->valB.alloc((size_t)p->lat.M * Lp, s);
+    h->pw.push_back(std::move(p));
+}
+
+bool pre_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
+bool post_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
+
+SliceTerm make_term(Pairwise &p, const float *blurred) {
+    SliceTerm t;
+    t.offset = p.lat.offset.p;
+    t.bary = p.lat.bary.p;
+    t.val = blurred;
+    t.norm = post_norm(p.ntype) ? p.norm.p : nullptr;
+    t.compat = p.compat.p;
+    t.potts_w = p.potts_w;
+    t.alpha = 1.0f / (1.0f + powf(2.0f, (float)-p.lat.d));
+    t.d = p.lat.d;
+    t.compat_kind = p.compat_kind;
+    return t;
+}
+
+void start_inference(dcrf_handle *h) {
+    DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_terms = 0;
+    launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
+    h->q_valid = true;
+}
+
+void step_inference(dcrf_handle *h) {
+    DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "stepInference before startInference");
+    const bool seq = h->L <= 2;
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seq = seq ? 1 : 0;
+    for (auto &p : h->pw) {
+        const float *blurred =
+            filter_to_lattice(h, *p, h->Q.p, h->Lp, pre_norm(p->ntype), seq, p->valA.p, p->valB.p);
+        a.term[a.n_terms++] = make_term(*p, blurred);
+    }
+    launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
+}
+
+void emit_q(dcrf_handle *h, float *Q_out, int on_device) {
+    DCRF_REQUIRE(Q_out != nullptr, DCRF_EINVAL, "Q_out is NULL");
+    const int64_t n = total_ln(h);
+    if (on_device) {
+        launch_pm_to_ln(h->Q.p, Q_out, h->geom, h->L, h->Lp, h->stream);
+    } else {
+        DevBuf<float> stage;
+        stage.alloc(n, h->stream);
+        launch_pm_to_ln(h->Q.p, stage.p, h->geom, h->L, h->Lp, h->stream);
+        DCRF_CUDA(cudaMemcpyAsync(Q_out, stage.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+        DCRF_CUDA(cudaStreamSynchronize(h->stream));
+    }
+}
+
+void run_inference(dcrf_handle *h, int n_iter) {
+    DCRF_REQUIRE(n_iter >= 0, DCRF_EINVAL, "n_iter must be >= 0");
+    start_inference(h);
+    for (int it = 0; it < n_iter; it++) step_inference(h);
+}
+
+Pairwise &get_pw(dcrf_handle *h, int k) {
+    DCRF_REQUIRE(k >= 0 && k < (int)h->pw.size(), DCRF_EINVAL, "pairwise index out of range");
+    return *h->pw[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dcrf_last_error(void) { return t_error.c_str(); }
+const char *dcrf_version(void) { return "dcrf_b200 0.1 sm_100a"; }
+int64_t dcrf_launch_count(void) { return g_launches.load(); }
+
+int dcrf_create(int w, int h, int n_labels, int device, void *stream, dcrf_t **out) {
+    return guarded([&] { create_common(1, &w, &h, true, n_labels, device, stream, out); });
+}
+
+int dcrf_create_nd(int n_vars, int n_labels, int device, void *stream, dcrf_t **out) {
+    return guarded([&] {
+        int one = 1;
+        create_common(1, &n_vars, &one, false, n_labels, device, stream, out);
+    });
+}
+
+int dcrf_create_batch(int n_images, const int *w, const int *h, int n_labels, int device, void *stream,
+                      dcrf_t **out) {
+    return guarded([&] {
+        DCRF_REQUIRE(w && h, DCRF_EINVAL, "w/h arrays are NULL");
+        create_common(n_images, w, h, true, n_labels, device, stream, out);
+    });
+}
+
+void dcrf_destroy(dcrf_t *h) {
+    if (!h) return;
+    try {
+        DeviceGuard guard(h->device);
+        h->pw.clear();
+        h->unary.release();
+        h->Q.release();
+        h->d_w.release();
+        h->d_h.release();
+        h->d_pix_start.release();
+        if (h->own_stream) {
+            cudaStreamSynchronize(h->stream);
+            cudaStreamDestroy(h->stream);
+        }
+    } catch (...) {
+    }
+    delete h;
+}
+
+int dcrf_synchronize(dcrf_t *h) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DCRF_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && U, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+        DeviceGuard guard(h->device);
+        DevBuf<float> stage;
+        const float *src = to_device(h, U, (size_t)total_ln(h), on_device, stage);
+        launch_ln_to_pm(src, h->unary.p, h->geom, h->L, h->Lp, h->stream);
+        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));  // caller may reuse U
+        h->unary_set = true;
+        h->q_valid = false;
+    });
+}
+
+int dcrf_add_pairwise_gaussian(dcrf_t *h, float sx, float sy, int compat_kind, const float *compat,
+                               int kernel_type, int normalization_type) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DCRF_REQUIRE(h->has_geom, DCRF_ESTATE, "addPairwiseGaussian needs a 2-D model");
+        DeviceGuard guard(h->device);
+        FeatureSpec fs;
+        memset(&fs, 0, sizeof(fs));
+        fs.mode = 0;
+        fs.d = 2;
+        fs.s[0] = sx;
+        fs.s[1] = sy;
+        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
+    });
+}
+
+int dcrf_add_pairwise_bilateral(dcrf_t *h, float sx, float sy, float sr, float sg, float sb,
+                                const uint8_t *rgb, int on_device, int compat_kind, const float *compat,
+                                int kernel_type, int normalization_type) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && rgb, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->has_geom, DCRF_ESTATE, "addPairwiseBilateral needs a 2-D model");
+        DeviceGuard guard(h->device);
+        DevBuf<uint8_t> stage;
+        FeatureSpec fs;
+        memset(&fs, 0, sizeof(fs));
+        fs.mode = 1;
+        fs.d = 5;
+        fs.s[0] = sx; fs.s[1] = sy; fs.s[2] = sr; fs.s[3] = sg; fs.s[4] = sb;
+        fs.rgb = to_device(h, rgb, (size_t)h->geom.Ntot * 3, on_device, stage);
+        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
+        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dcrf_add_pairwise_energy(dcrf_t *h, const float *features, int d, int on_device, int compat_kind,
+                             const float *compat, int kernel_type, int normalization_type) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && features, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->geom.B == 1, DCRF_ESTATE, "addPairwiseEnergy is single-image only");
+        DCRF_REQUIRE(d >= 1 && d <= kMaxD, DCRF_EINVAL, "feature dimension d must be in [1, 7]");
+        DeviceGuard guard(h->device);
+        DevBuf<float> stage;
+        FeatureSpec fs;
+        memset(&fs, 0, sizeof(fs));
+        fs.mode = 2;
+        fs.d = d;
+        fs.features = to_device(h, features, (size_t)h->geom.Ntot * d, on_device, stage);
+        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
+        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int dcrf_inference(dcrf_t *h, int n_iter, float *Q_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DeviceGuard guard(h->device);
+        run_inference(h, n_iter);
+        emit_q(h, Q_out, on_device);
+    });
+}
+
+int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
+        DeviceGuard guard(h->device);
+        run_inference(h, n_iter);
+        const int64_t N = h->geom.Ntot;
+        if (on_device) {
+            launch_argmax(h->Q.p, labels_out, N, h->L, h->Lp, h->stream);
+        } else {
+            DevBuf<int32_t> stage;
+            stage.alloc(N, h->stream);
+            launch_argmax(h->Q.p, stage.p, N, h->L, h->Lp, h->stream);
+            DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost,
+                                      h->stream));
+            DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    });
+}
+
+int dcrf_start_inference(dcrf_t *h) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DeviceGuard guard(h->device);
+        start_inference(h);
+    });
+}
+
+int dcrf_step_inference(dcrf_t *h) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DeviceGuard guard(h->device);
+        step_inference(h);
+    });
+}
+
+int dcrf_get_q(dcrf_t *h, float *Q_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call startInference first");
+        DeviceGuard guard(h->device);
+        emit_q(h, Q_out, on_device);
+    });
+}
+
+int dcrf_set_q(dcrf_t *h, const float *Q_in, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && Q_in, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+        DeviceGuard guard(h->device);
+        DevBuf<float> stage;
+        const float *src = to_device(h, Q_in, (size_t)total_ln(h), on_device, stage);
+        launch_ln_to_pm(src, h->Q.p, h->geom, h->L, h->Lp, h->stream);
+        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        h->q_valid = true;
+    });
+}
+
+int dcrf_kl_divergence(dcrf_t *h, double *kl_out) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && kl_out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call startInference first");
+        DeviceGuard guard(h->device);
+        cudaStream_t s = h->stream;
+        const int64_t Ntot = h->geom.Ntot;
+        const bool seq = h->L <= 2;
+        std::vector<DevBuf<float>> outs(h->pw.size());
+        const float *ptrs[kMaxPairwise] = {nullptr, nullptr, nullptr, nullptr};
+        for (size_t k = 0; k < h->pw.size(); k++) {
+            Pairwise &p = *h->pw[k];
+            const float *blurred =
+                filter_to_lattice(h, p, h->Q.p, h->Lp, pre_norm(p.ntype), seq, p.valA.p, p.valB.p);
+            outs[k].alloc((size_t)Ntot * h->Lp, s);
+            launch_slice_pairwise_only(make_term(p, blurred), outs[k].p, Ntot, h->L, h->Lp, s);
+            ptrs[k] = outs[k].p;
+        }
+        DevBuf<double> d_out;
+        d_out.alloc(1, s);
+        launch_kl(h->Q.p, h->unary.p, ptrs, (int)h->pw.size(), Ntot, h->L, h->Lp, d_out.p, s);
+        DCRF_CUDA(cudaMemcpyAsync(kl_out, d_out.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int dcrf_num_pairwise(dcrf_t *h, int *n_out) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && n_out, DCRF_EINVAL, "NULL argument");
+        *n_out = (int)h->pw.size();
+    });
+}
+
+int dcrf_lattice_info(dcrf_t *h, int kernel, int *d_out, int64_t *M_out, int64_t *M_per_image) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        Pairwise &p = get_pw(h, kernel);
+        if (d_out) *d_out = p.lat.d;
+        if (M_out) *M_out = p.lat.M;
+        if (M_per_image)
+            for (int b = 0; b < h->geom.B; b++) M_per_image[b] = p.lat.vert_start[b + 1] - p.lat.vert_start[b];
+    });
+}
+
+int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t *offsets, float *bary,
+                        int32_t *neighbours, float *norm) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DCRF_REQUIRE(image >= 0 && image < h->geom.B, DCRF_EINVAL, "image index out of range");
+        DeviceGuard guard(h->device);
+        Pairwise &p = get_pw(h, kernel);
+        cudaStream_t s = h->stream;
+        const int d = p.lat.d, d1 = d + 1;
+        const int64_t p0 = h->geom.pix_start[image], Nb = h->geom.pix_start[image + 1] - p0;
+        const int64_t v0 = p.lat.vert_start[image], Mb = p.lat.vert_start[image + 1] - v0;
+        std::vector<int16_t> k8;
+        std::vector<int2> nb;
+        if (keys) {
+            k8.resize((size_t)Mb * 8);
+            DCRF_CUDA(cudaMemcpyAsync(k8.data(), p.lat.vkeys.p + v0 * 8, sizeof(int16_t) * Mb * 8,
+                                      cudaMemcpyDeviceToHost, s));
+        }
+        if (offsets)
+            DCRF_CUDA(cudaMemcpyAsync(offsets, p.lat.offset.p + p0 * d1, sizeof(int32_t) * Nb * d1,
+                                      cudaMemcpyDeviceToHost, s));
+        if (bary)
+            DCRF_CUDA(cudaMemcpyAsync(bary, p.lat.bary.p + p0 * d1, sizeof(float) * Nb * d1,
+                                      cudaMemcpyDeviceToHost, s));
+        if (neighbours) {
+            nb.resize((size_t)Mb * d1);
+            for (int j = 0; j < d1; j++)
+                DCRF_CUDA(cudaMemcpyAsync(nb.data() + (size_t)j * Mb, p.lat.neigh.p + (int64_t)j * p.lat.M + v0,
+                                          sizeof(int2) * Mb, cudaMemcpyDeviceToHost, s));
+        }
+        if (norm) {
+            DCRF_REQUIRE(p.norm.p != nullptr, DCRF_ESTATE, "kernel has no norm (NO_NORMALIZATION)");
+            DCRF_CUDA(cudaMemcpyAsync(norm, p.norm.p + p0, sizeof(float) * Nb, cudaMemcpyDeviceToHost, s));
+        }
+        DCRF_CUDA(cudaStreamSynchronize(s));
+        if (keys)
+            for (int64_t v = 0; v < Mb; v++)
+                for (int i = 0; i < d; i++) keys[v * d + i] = k8[(size_t)v * 8 + i];
+        if (offsets)
+            for (int64_t i = 0; i < Nb * d1; i++) offsets[i] -= (int32_t)v0;
+        if (neighbours)
+            for (int64_t i = 0; i < Mb * d1; i++) {
+                neighbours[2 * i + 0] = nb[i].x >= 0 ? nb[i].x - (int32_t)v0 : -1;
+                neighbours[2 * i + 1] = nb[i].y >= 0 ? nb[i].y - (int32_t)v0 : -1;
+            }
+    });
+}
+
+int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int value_size) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && in && out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->geom.B == 1, DCRF_ESTATE, "lattice_filter is single-image only");
+        DCRF_REQUIRE(value_size >= 1 && value_size <= 128, DCRF_EINVAL, "value_size must be in [1, 128]");
+        DeviceGuard guard(h->device);
+        Pairwise &p = get_pw(h, kernel);
+        cudaStream_t s = h->stream;
+        const int64_t N = h->geom.Ntot;
+        const int vs = value_size, vp = ((vs + 3) / 4) * 4;
+        const bool seq = vs <= 2;
+        DevBuf<float> ln, pm, a, b, sl;
+        ln.alloc((size_t)N * vs, s);
+        pm.alloc((size_t)N * vp, s);
+        a.alloc((size_t)p.lat.M * vp, s);
+        b.alloc((size_t)p.lat.M * vp, s);
+        sl.alloc((size_t)N * vp, s);
+        DCRF_CUDA(cudaMemcpyAsync(ln.p, in, sizeof(float) * N * vs, cudaMemcpyHostToDevice, s));
+        launch_ln_to_pm(ln.p, pm.p, h->geom, vs, vp, s);
+        const float *blurred = filter_to_lattice(h, p, pm.p, vp, false, seq, a.p, b.p);
+        launch_slice_plain(p.lat, blurred, sl.p, N, vp, seq, s);
+        launch_pm_to_ln(sl.p, ln.p, h->geom, vs, vp, s);
+        DCRF_CUDA(cudaMemcpyAsync(out, ln.p, sizeof(float) * N * vs, cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+}  // extern "C"

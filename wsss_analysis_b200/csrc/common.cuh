@@ -1,0 +1,172 @@
+// common.cuh -- shared declarations of the dcrf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/dcrf_b200.h"
+
+namespace dcrf {
+
+constexpr int kMaxD = 7;        // lattice feature dimension supported (rank nibbles pack into 32 bits)
+constexpr int kMaxPairwise = 4; // pairwise kernels fused into one slice launch
+constexpr int kNumSMs = 148;    // B200
+
+extern std::atomic<int64_t> g_launches;
+void set_error(const std::string &msg);
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define DCRF_CUDA(expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::dcrf::Error{DCRF_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)}; \
+    } while (0)
+
+#define DCRF_REQUIRE(cond, code, message)                  \
+    do {                                                   \
+        if (!(cond)) throw ::dcrf::Error{(code), (message)}; \
+    } while (0)
+
+// count + check a kernel launch
+#define DCRF_LAUNCHED()                                \
+    do {                                               \
+        ::dcrf::g_launches.fetch_add(1);               \
+        DCRF_CUDA(cudaGetLastError());                 \
+    } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync pool: allocation is cheap after warm-up).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    void alloc(size_t count, cudaStream_t stream) {
+        release();
+        s = stream;
+        n = count;
+        if (count) DCRF_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), stream));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// lattice construction (lattice_build.cu)
+// ---------------------------------------------------------------------------------------------
+struct FeatureSpec {
+    int mode;        // 0 = gaussian (x/sx, y/sy), 1 = bilateral (+ r/sr, g/sg, b/sb), 2 = explicit (d, N)
+    int d;
+    float s[5];      // sx, sy, sr, sg, sb
+    const uint8_t *rgb;    // device, concatenated (N, 3)            (mode 1)
+    const float *features; // device, row-major (d, N)               (mode 2)
+};
+
+struct BatchGeom {
+    int B;
+    int64_t Ntot;
+    const int *d_w, *d_h;          // device [B]
+    const int *d_pix_start;        // device [B+1]
+    std::vector<int> w, h;
+    std::vector<int64_t> pix_start; // host [B+1]
+};
+
+// Result of building one lattice over the whole batch; vertex ids are GLOBAL over the batch and,
+// inside each image, follow the reference first-occurrence numbering.
+struct Lattice {
+    int d = 0;
+    int64_t M = 0;                 // total vertices
+    int64_t E = 0;                 // Ntot * (d+1) entries
+    std::vector<int64_t> vert_start; // host [B+1]
+    DevBuf<int32_t> offset;        // [E] vertex id of entry e = p*(d+1)+r
+    DevBuf<float> bary;            // [E]
+    DevBuf<int2> neigh;            // [(d+1) * M] (n1, n2), -1 = absent
+    DevBuf<int16_t> vkeys;         // [M * 8] key of each vertex (first d shorts used)
+    DevBuf<int32_t> csr_start;     // [M+1] rows of the transposed incidence (splat as a gather)
+    DevBuf<int32_t> csr_pix;       // [E] pixel of each sorted entry (ascending entry order per row)
+    DevBuf<float> csr_w;           // [E] barycentric weight of each sorted entry
+};
+
+void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// filtering + mean field (filter.cu)
+// ---------------------------------------------------------------------------------------------
+// one pairwise term as seen by the fused slice/softmax kernel
+struct SliceTerm {
+    const int32_t *offset;
+    const float *bary;
+    const float *val;     // blurred lattice values [M * Lp]
+    const float *norm;    // [Ntot] or nullptr (no post-scaling)
+    const float *compat;  // device: Potts -> unused, diagonal -> [L], matrix -> [L*L]
+    float potts_w;
+    float alpha;
+    int d;
+    int compat_kind;
+};
+struct SliceArgs {
+    SliceTerm term[kMaxPairwise];
+    int n_terms;
+    int seq;  // value_size <= 2 association (A.4)
+};
+
+// values <- splat of (pre ? norm (.) Q : Q)       (A.4 splat, A.5 pre-scaling)
+void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, float *val, int Lp,
+                  cudaStream_t s);
+// out <- in + 0.5 (in[n1] + in[n2]) along axis j  (A.4 blur)
+void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
+                 cudaStream_t s);
+// Q <- softmax_L( -U - sum_k compat_k( norm_k (.) slice_k ) )   (A.4 slice, A.5, A.6, A.7)
+void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int64_t Ntot, int L,
+                          int Lp, cudaStream_t s);
+// plain slice of one lattice into a pixel-major buffer: out[p] = sum_r w v alpha (seq selects the
+// value_size<=2 association)
+void launch_slice_plain(const Lattice &lat, const float *val, float *out, int64_t Ntot, int Lp,
+                        bool seq, cudaStream_t s);
+// norm[p] <- f(slice value of the all-ones filter) per normalisation type (A.5)
+void launch_norm_finalize(const float *sliced, int Lp, float *norm, int64_t Ntot, int ntype,
+                          cudaStream_t s);
+void launch_fill_ones_col0(float *buf, int64_t Ntot, int Lp, cudaStream_t s);
+// (L, N_b) row-major blocks  <->  (Ntot, Lp) pixel-major
+void launch_ln_to_pm(const float *ln, float *pm, const BatchGeom &g, int L, int Lp, cudaStream_t s);
+void launch_pm_to_ln(const float *pm, float *ln, const BatchGeom &g, int L, int Lp, cudaStream_t s);
+void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s);
+// deterministic double-precision KL terms
+void launch_kl(const float *Q, const float *unary, const float *const *pair_out, int n_pair,
+               int64_t Ntot, int L, int Lp, double *out, cudaStream_t s);
+// pairwise_out <- compat( norm (.) slice ) for one term (used by klDivergence)
+void launch_slice_pairwise_only(const SliceTerm &t, float *out, int64_t Ntot, int L, int Lp,
+                                cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// device-wide primitives (primitives.cu)
+// ---------------------------------------------------------------------------------------------
+// out[i] = exclusive prefix sum of in[0..i), out[n] = total.  in/out may alias.  int32.
+void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
+// stable LSD radix sort of (key, value) pairs on the low `bits` bits of key.  Results end in
+// keys_a / vals_a; *_b are scratch of the same size.
+void radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                      int64_t n, int bits, cudaStream_t s);
+
+}  // namespace dcrf

@@ -1,0 +1,503 @@
+// lattice_build.cu -- permutohedral lattice construction on the GPU (sm_100a).
+//
+// Replaces the set-up half of pydensecrf's addPairwiseGaussian / addPairwiseBilateral /
+// addPairwiseEnergy (call sites: /root/reference/03c_hsn/utilities.py:435,439-440), i.e. the
+// sequential `Permutohedral::init` [EXT] specified in SURVEY.md Appendix A.3:
+//   K1  point kernel : features -> elevate -> nearest remainder-0 point -> rank -> barycentric
+//   K2  hash insert  : open-addressing table of lattice keys, slot value = min entry index
+//   K3  numbering    : first-occurrence flags + exclusive scan  => the reference's vertex ids
+//   K4  assign       : offsets, vertex keys, table slot -> vertex id
+//   K5  neighbours   : +-1 neighbours along each of the d+1 axes by table lookup
+//   K6  CSR          : stable radix sort of entries by vertex id => rows of the transposed
+//                      incidence matrix in ascending entry order (deterministic splat)
+//
+// Bit-exactness: the coordinate math uses explicit round-to-nearest intrinsics (__fmul_rn, ...)
+// so nvcc can never contract it into FMAs, true IEEE division for the features, and the same
+// float/double/int mixing as the specification.  The vertex numbering is made independent of the
+// (racy) insertion order: every table slot ends up holding the SMALLEST entry index e = p*(d+1)+r
+// that carries its key (atomicMin), and ids are the scan of "I am the first occurrence" flags --
+// exactly "id = rank of the key's first occurrence in pixel-major, remainder-minor scan order".
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dcrf {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct GeomDev {
+    const int *w, *h, *pix_start;  // [B], [B], [B+1]
+    int B;
+};
+
+__device__ __forceinline__ int find_image(const int *__restrict__ start, int B, int64_t x) {
+    // largest b with start[b] <= x
+    int lo = 0, hi = B - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)start[mid] <= x) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <int D>
+struct Scale {
+    float s[D];
+};
+
+// canonical simplex entry (A.3 step 7): canon[r][k] = r for k <= D - r, else r - (D+1)
+template <int D>
+__device__ __forceinline__ int canon(int r, int k) {
+    return (k <= D - r) ? r : r - (D + 1);
+}
+
+// key of entry (pixel record, remainder r): key[i] = rem0[i] + canon[r][rank[i]], i < D
+template <int D>
+__device__ __forceinline__ void entry_key(const int4 rem, uint32_t rankpack, int r, short key[8]) {
+    const short *rm = reinterpret_cast<const short *>(&rem);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < D) {
+            int rk = (rankpack >> (4 * i)) & 15;
+            key[i] = (short)(rm[i] + canon<D>(r, rk));
+        } else {
+            key[i] = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ int4 pack_key(const short key[8]) {
+    int4 v;
+    v.x = (int)(((uint32_t)(uint16_t)key[0]) | ((uint32_t)(uint16_t)key[1] << 16));
+    v.y = (int)(((uint32_t)(uint16_t)key[2]) | ((uint32_t)(uint16_t)key[3] << 16));
+    v.z = (int)(((uint32_t)(uint16_t)key[4]) | ((uint32_t)(uint16_t)key[5] << 16));
+    v.w = (int)(((uint32_t)(uint16_t)key[6]) | ((uint32_t)(uint16_t)key[7] << 16));
+    return v;
+}
+
+__device__ __forceinline__ bool key_eq(const int4 a, const int4 b) {
+    return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+}
+
+__device__ __forceinline__ uint32_t key_hash(const int4 k) {
+    uint32_t h = 0x811C9DC5u;
+    h = (h ^ (uint32_t)k.x) * 0x01000193u;
+    h ^= h >> 15;
+    h = (h ^ (uint32_t)k.y) * 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h = (h ^ (uint32_t)k.z) * 0xC2B2AE35u;
+    h ^= h >> 16;
+    h = (h ^ (uint32_t)k.w) * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one thread per pixel (Appendix A.2 + A.3 steps 2-6)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kThreads) lattice_point_kernel(
+    GeomDev g, int64_t Ntot, int mode, float sx, float sy, float sr, float sg, float sb,
+    const uint8_t *__restrict__ rgb, const float *__restrict__ features, Scale<D> scale,
+    int4 *__restrict__ rec_rem, uint32_t *__restrict__ rec_rank, float *__restrict__ bary_out) {
+    const int64_t gp = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (gp >= Ntot) return;
+    float f[D];
+    if (mode == 2) {
+#pragma unroll
+        for (int j = 0; j < D; j++) f[j] = features[(int64_t)j * Ntot + gp];
+    } else {
+        const int b = find_image(g.pix_start, g.B, gp);
+        const int lp = (int)(gp - g.pix_start[b]);
+        const int W = g.w[b];
+        const int y = lp / W, x = lp - y * W;
+        // A.2: float32 true division of an integer by a float32 parameter
+        if (D >= 1) f[0] = __fdiv_rn((float)x, sx);
+        if (D >= 2) f[1] = __fdiv_rn((float)y, sy);
+        if (mode == 1 && D >= 5) {
+            f[2] = __fdiv_rn((float)rgb[gp * 3 + 0], sr);
+            f[3] = __fdiv_rn((float)rgb[gp * 3 + 1], sg);
+            f[4] = __fdiv_rn((float)rgb[gp * 3 + 2], sb);
+        }
+    }
+    // step 2: elevate (no FMA)
+    float e[D + 1];
+    float sm = 0.f;
+#pragma unroll
+    for (int j = D; j > 0; j--) {
+        float cf = __fmul_rn(f[j - 1], scale.s[j - 1]);
+        e[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
+        sm = __fadd_rn(sm, cf);
+    }
+    e[0] = sm;
+    // step 3: nearest remainder-0 point; sum is an int accumulator of float terms
+    const float down_factor = 1.0f / (float)(D + 1);
+    const float up_factor = (float)(D + 1);
+    float rem0[D + 1];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        float v = __fmul_rn(down_factor, e[i]);
+        float up = __fmul_rn(ceilf(v), up_factor);
+        float down = __fmul_rn(floorf(v), up_factor);
+        int rd2;
+        if (__fsub_rn(up, e[i]) < __fsub_rn(e[i], down)) rd2 = (short)(int)up;
+        else rd2 = (short)(int)down;
+        rem0[i] = (float)rd2;
+        sum = (int)__fadd_rn((float)sum, __fmul_rn((float)rd2, down_factor));
+    }
+    // step 4: rank
+    int rank[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; i++) rank[i] = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        float di = __fsub_rn(e[i], rem0[i]);
+#pragma unroll
+        for (int j = i + 1; j <= D; j++) {
+            if (di < __fsub_rn(e[j], rem0[j])) rank[i]++;
+            else rank[j]++;
+        }
+    }
+    // step 5: re-project
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        rank[i] += sum;
+        if (rank[i] < 0) {
+            rank[i] += D + 1;
+            rem0[i] = __fadd_rn(rem0[i], (float)(D + 1));
+        } else if (rank[i] > D) {
+            rank[i] -= D + 1;
+            rem0[i] = __fsub_rn(rem0[i], (float)(D + 1));
+        }
+    }
+    // step 6: barycentric (updates applied in i order, like the sequential code)
+    float bc[D + 2];
+#pragma unroll
+    for (int i = 0; i <= D + 1; i++) bc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+        float v = __fmul_rn(__fsub_rn(e[i], rem0[i]), down_factor);
+        int idx = D - rank[i];
+#pragma unroll
+        for (int k = 0; k <= D + 1; k++) {
+            if (k == idx) bc[k] = __fadd_rn(bc[k], v);
+            if (k == idx + 1) bc[k] = __fsub_rn(bc[k], v);
+        }
+    }
+    bc[0] = (float)((double)bc[0] + (1.0 + (double)bc[D + 1]));
+#pragma unroll
+    for (int r = 0; r <= D; r++) bary_out[gp * (D + 1) + r] = bc[r];
+    // pixel record: first D coordinates of rem0 as int16, first D ranks as nibbles
+    short rm[8];
+    uint32_t rp = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < D) {
+            rm[i] = (short)(int)rem0[i];
+            rp |= (uint32_t)(rank[i] & 15) << (4 * i);
+        } else {
+            rm[i] = 0;
+        }
+    }
+    rec_rem[gp] = pack_key(rm);
+    rec_rank[gp] = rp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: hash insert.  One thread per pixel, d+1 inserts.  table[] holds entry indices (-1 = empty);
+// a slot's key never changes once claimed, only its representative shrinks (atomicMin).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kThreads) hash_insert_kernel(
+    GeomDev g, int64_t Ntot, const int64_t *__restrict__ tab_start, const int *__restrict__ tab_mask,
+    const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank, int32_t *table,
+    int32_t *__restrict__ slot_of) {
+    const int64_t gp = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (gp >= Ntot) return;
+    const int b = find_image(g.pix_start, g.B, gp);
+    int32_t *tab = table + tab_start[b];
+    const uint32_t mask = (uint32_t)tab_mask[b];
+    const int4 rem = rec_rem[gp];
+    const uint32_t rp = rec_rank[gp];
+#pragma unroll 1
+    for (int r = 0; r <= D; r++) {
+        short key[8];
+        entry_key<D>(rem, rp, r, key);
+        const int4 pk = pack_key(key);
+        const int32_t e = (int32_t)(gp * (D + 1) + r);
+        uint32_t h = key_hash(pk) & mask;
+        for (;;) {
+            int32_t cur = tab[h];
+            if (cur < 0) {
+                cur = atomicCAS(&tab[h], -1, e);
+                if (cur < 0) break;  // claimed
+            }
+            // occupied by entry `cur`: same key?
+            const int64_t cp = cur / (D + 1);
+            const int cr = cur - (int32_t)cp * (D + 1);
+            short ck[8];
+            entry_key<D>(rec_rem[cp], rec_rank[cp], cr, ck);
+            if (key_eq(pack_key(ck), pk)) {
+                if (e < cur) atomicMin(&tab[h], e);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        slot_of[e] = (int32_t)h;
+    }
+}
+
+// K3: flag[e] = 1 iff entry e is the first occurrence of its key
+template <int D>
+__global__ void __launch_bounds__(kThreads) first_flag_kernel(
+    GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
+    const int32_t *__restrict__ slot_of, int32_t *__restrict__ flag) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    const int b = find_image(g.pix_start, g.B, e / (D + 1));
+    flag[e] = (table[tab_start[b] + slot_of[e]] == (int32_t)e) ? 1 : 0;
+}
+
+// K4a: offsets for all entries; first occurrences also publish their vertex (rep entry + key)
+template <int D>
+__global__ void __launch_bounds__(kThreads) assign_kernel(
+    GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
+    const int32_t *__restrict__ slot_of, const int32_t *__restrict__ scanned,
+    const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
+    int32_t *__restrict__ offset, int32_t *__restrict__ vert_rep, int4 *__restrict__ vkeys) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    const int64_t gp = e / (D + 1);
+    const int b = find_image(g.pix_start, g.B, gp);
+    const int32_t rep = table[tab_start[b] + slot_of[e]];
+    const int32_t id = scanned[rep];
+    offset[e] = id;
+    if (rep == (int32_t)e) {
+        vert_rep[id] = (int32_t)e;
+        short key[8];
+        entry_key<D>(rec_rem[gp], rec_rank[gp], (int)(e - gp * (D + 1)), key);
+        vkeys[id] = pack_key(key);
+    }
+}
+
+// K4b: table slot: representative entry -> vertex id (one thread per vertex)
+template <int D>
+__global__ void __launch_bounds__(kThreads) table_to_id_kernel(
+    GeomDev g, int64_t M, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ vert_rep,
+    const int32_t *__restrict__ slot_of, int32_t *__restrict__ table) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= M) return;
+    const int32_t e = vert_rep[v];
+    const int b = find_image(g.pix_start, g.B, e / (D + 1));
+    table[tab_start[b] + slot_of[e]] = (int32_t)v;
+}
+
+// vert_start[b] = number of first occurrences before image b's first entry
+__global__ void vert_start_kernel(const int *__restrict__ pix_start, int B, int d1,
+                                  const int32_t *__restrict__ scanned, int32_t *__restrict__ vert_start) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= B) vert_start[b] = scanned[(int64_t)pix_start[b] * d1];
+}
+
+// K5: neighbours.  One thread per (axis j, vertex v); table now holds vertex ids.
+template <int D>
+__global__ void __launch_bounds__(kThreads) neighbour_kernel(
+    int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
+    const int *__restrict__ tab_mask, const int32_t *__restrict__ table,
+    const int4 *__restrict__ vkeys, int2 *__restrict__ neigh) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= M * (D + 1)) return;
+    const int j = (int)(t / M);
+    const int64_t v = t - (int64_t)j * M;
+    const int b = find_image(vert_start, B, v);
+    const int32_t *tab = table + tab_start[b];
+    const uint32_t mask = (uint32_t)tab_mask[b];
+    const int4 kv = vkeys[v];
+    const short *key = reinterpret_cast<const short *>(&kv);
+    int res[2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        short nk[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < D) {
+                int delta = (side == 0) ? -1 : 1;
+                if (k == j) delta = (side == 0) ? D : -D;
+                nk[k] = (short)(key[k] + delta);
+            } else {
+                nk[k] = 0;
+            }
+        }
+        const int4 pk = pack_key(nk);
+        uint32_t h = key_hash(pk) & mask;
+        int found = -1;
+        for (;;) {
+            int32_t cur = tab[h];
+            if (cur < 0) break;
+            if (key_eq(vkeys[cur], pk)) { found = cur; break; }
+            h = (h + 1) & mask;
+        }
+        res[side] = found;
+    }
+    neigh[(int64_t)j * M + v] = make_int2(res[0], res[1]);
+}
+
+__global__ void __launch_bounds__(kThreads) iota_copy_kernel(const int32_t *__restrict__ offset,
+                                                             uint32_t *__restrict__ keys,
+                                                             uint32_t *__restrict__ vals, int64_t E) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    keys[e] = (uint32_t)offset[e];
+    vals[e] = (uint32_t)e;
+}
+
+// K6 epilogue: sorted (vertex, entry) pairs -> CSR rows
+__global__ void __launch_bounds__(kThreads) csr_finalize_kernel(
+    const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
+    const float *__restrict__ bary, int d1, int64_t E, int64_t M, int32_t *__restrict__ csr_start,
+    int32_t *__restrict__ csr_pix, float *__restrict__ csr_w) {
+    const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= E) return;
+    const uint32_t v = skeys[s];
+    const uint32_t e = svals[s];
+    csr_pix[s] = (int32_t)(e / (uint32_t)d1);
+    csr_w[s] = bary[e];
+    if (s == 0 || skeys[s - 1] != v) csr_start[v] = (int32_t)s;
+    if (s == E - 1) csr_start[M] = (int32_t)E;
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+template <int D>
+void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {
+    const int B = g.B;
+    const int64_t Ntot = g.Ntot;
+    const int d1 = D + 1;
+    const int64_t E = Ntot * d1;
+    DCRF_REQUIRE(E < (int64_t)2147483000, DCRF_EINVAL, "batch too large: N*(d+1) must stay below 2^31");
+    out.d = D;
+    out.E = E;
+    GeomDev gd{g.d_w, g.d_h, g.d_pix_start, B};
+
+    // A.3 step 1 on the host: double math stored as float (identical to the specification)
+    Scale<D> scale;
+    const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (double)d1);
+    for (int i = 0; i < D; i++)
+        scale.s[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * (double)inv_std_dev);
+
+    DevBuf<int4> rec_rem;
+    DevBuf<uint32_t> rec_rank;
+    rec_rem.alloc(Ntot, s);
+    rec_rank.alloc(Ntot, s);
+    out.bary.alloc(E, s);
+    const int nbp = ceil_div(Ntot, kThreads);
+    lattice_point_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, f.mode, f.s[0], f.s[1], f.s[2], f.s[3],
+                                                    f.s[4], f.rgb, f.features, scale, rec_rem.p,
+                                                    rec_rank.p, out.bary.p);
+    DCRF_LAUNCHED();
+
+    // per-image table regions: capacity = pow2 >= 2 * N_b * (d+1)
+    std::vector<int64_t> tab_start(B + 1, 0);
+    std::vector<int> tab_mask(B);
+    for (int b = 0; b < B; b++) {
+        int64_t need = 2 * (g.pix_start[b + 1] - g.pix_start[b]) * d1;
+        int64_t cap = 64;
+        while (cap < need) cap <<= 1;
+        tab_mask[b] = (int)(cap - 1);
+        tab_start[b + 1] = tab_start[b] + cap;
+    }
+    DevBuf<int64_t> d_tab_start;
+    DevBuf<int> d_tab_mask;
+    d_tab_start.alloc(B + 1, s);
+    d_tab_mask.alloc(B, s);
+    DCRF_CUDA(cudaMemcpyAsync(d_tab_start.p, tab_start.data(), sizeof(int64_t) * (B + 1),
+                              cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaMemcpyAsync(d_tab_mask.p, tab_mask.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    DevBuf<int32_t> table;
+    table.alloc(tab_start[B], s);
+    DCRF_CUDA(cudaMemsetAsync(table.p, 0xFF, sizeof(int32_t) * tab_start[B], s));
+
+    DevBuf<int32_t> slot_of;
+    slot_of.alloc(E, s);
+    hash_insert_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, d_tab_start.p, d_tab_mask.p, rec_rem.p,
+                                                  rec_rank.p, table.p, slot_of.p);
+    DCRF_LAUNCHED();
+
+    DevBuf<int32_t> scanned;
+    scanned.alloc(E + 1, s);
+    const int nbe = ceil_div(E, kThreads);
+    first_flag_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p);
+    DCRF_LAUNCHED();
+    exclusive_scan_i32(scanned.p, scanned.p, E, s);
+
+    // vertex counts: total + per image (host needs them to size everything else)
+    DevBuf<int32_t> d_vert_start;
+    d_vert_start.alloc(B + 1, s);
+    vert_start_kernel<<<ceil_div(B + 1, 128), 128, 0, s>>>(g.d_pix_start, B, d1, scanned.p, d_vert_start.p);
+    DCRF_LAUNCHED();
+    std::vector<int32_t> h_vs(B + 1);
+    DCRF_CUDA(cudaMemcpyAsync(h_vs.data(), d_vert_start.p, sizeof(int32_t) * (B + 1),
+                              cudaMemcpyDeviceToHost, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));
+    out.vert_start.assign(h_vs.begin(), h_vs.end());
+    const int64_t M = h_vs[B];
+    out.M = M;
+
+    out.offset.alloc(E, s);
+    DevBuf<int32_t> vert_rep;
+    vert_rep.alloc(M, s);
+    out.vkeys.alloc((size_t)M * 8, s);
+    int4 *vkeys4 = reinterpret_cast<int4 *>(out.vkeys.p);
+    assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
+                                             rec_rem.p, rec_rank.p, out.offset.p, vert_rep.p, vkeys4);
+    DCRF_LAUNCHED();
+    table_to_id_kernel<D><<<ceil_div(M, kThreads), kThreads, 0, s>>>(gd, M, d_tab_start.p, vert_rep.p,
+                                                                    slot_of.p, table.p);
+    DCRF_LAUNCHED();
+
+    out.neigh.alloc((size_t)M * d1, s);
+    neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
+        M, B, d_vert_start.p, d_tab_start.p, d_tab_mask.p, table.p, vkeys4, out.neigh.p);
+    DCRF_LAUNCHED();
+
+    // transposed incidence rows: stable sort of entries by vertex id
+    DevBuf<uint32_t> ka, va, kb, vb;
+    ka.alloc(E, s); va.alloc(E, s); kb.alloc(E, s); vb.alloc(E, s);
+    iota_copy_kernel<<<nbe, kThreads, 0, s>>>(out.offset.p, ka.p, va.p, E);
+    DCRF_LAUNCHED();
+    int bits = 1;
+    while (((int64_t)1 << bits) < M) bits++;
+    radix_sort_pairs(ka.p, va.p, kb.p, vb.p, E, bits, s);
+    out.csr_start.alloc(M + 1, s);
+    out.csr_pix.alloc(E, s);
+    out.csr_w.alloc(E, s);
+    csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(ka.p, va.p, out.bary.p, d1, E, M, out.csr_start.p,
+                                                out.csr_pix.p, out.csr_w.p);
+    DCRF_LAUNCHED();
+}
+
+}  // namespace
+
+void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {
+    switch (f.d) {
+        case 1: build_impl<1>(g, f, out, s); break;
+        case 2: build_impl<2>(g, f, out, s); break;
+        case 3: build_impl<3>(g, f, out, s); break;
+        case 4: build_impl<4>(g, f, out, s); break;
+        case 5: build_impl<5>(g, f, out, s); break;
+        case 6: build_impl<6>(g, f, out, s); break;
+        case 7: build_impl<7>(g, f, out, s); break;
+        default:
+            throw Error{DCRF_EINVAL, "feature dimension d must be in [1, 7]"};
+    }
+}
+
+}  // namespace dcrf

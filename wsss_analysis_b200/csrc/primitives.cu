@@ -1,0 +1,232 @@
+// primitives.cu -- hand-written device-wide exclusive scan and stable LSD radix sort (sm_100a).
+// Used only by lattice construction (vertex numbering and the splat's transposed incidence rows).
+// Everything here is integer work: results are bit-deterministic.
+#include "common.cuh"
+
+namespace dcrf {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one value per thread over the block; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    __shared__ int block_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = warp_inclusive_scan(v);
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+        int sinc = warp_inclusive_scan(s);
+        if (lane < kScanThreads / 32) warp_sums[lane] = sinc - s;
+        if (lane == kScanThreads / 32 - 1) block_total = sinc;
+    }
+    __syncthreads();
+    int r = inc - v + warp_sums[warp];
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int32_t *__restrict__ in,
+                                                                   int32_t *__restrict__ sums,
+                                                                   int64_t n) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int s = 0;
+    if (base + kScanItems <= n) {
+        const int4 *p = reinterpret_cast<const int4 *>(in + base);
+#pragma unroll
+        for (int i = 0; i < kScanItems / 4; i++) {
+            int4 v = p[i];
+            s += v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (int i = 0; i < kScanItems; i++)
+            if (base + i < n) s += in[base + i];
+    }
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// carry == nullptr: single-tile scan (n <= kScanTile, one block)
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const int32_t *__restrict__ in,
+                                                                  int32_t *__restrict__ out,
+                                                                  const int32_t *__restrict__ carry,
+                                                                  int64_t n, int write_total) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    if (base + kScanItems <= n) {
+        const int4 *p = reinterpret_cast<const int4 *>(in + base);
+#pragma unroll
+        for (int i = 0; i < kScanItems / 4; i++) {
+            int4 t = p[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) v[i] = (base + i < n) ? in[base + i] : 0;
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) s += v[i];
+    int total;
+    int run = block_exclusive_scan(s, &total) + (carry ? carry[blockIdx.x] : 0);
+    // in and out may alias: every thread has read all of its inputs before any write of its range
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int t = v[i];
+        v[i] = run;
+        run += t;
+    }
+    if (base + kScanItems <= n) {
+        int4 *q = reinterpret_cast<int4 *>(out + base);
+#pragma unroll
+        for (int i = 0; i < kScanItems / 4; i++)
+            q[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++)
+            if (base + i < n) out[base + i] = v[i];
+    }
+    if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) out[n] = run;
+}
+
+void scan_rec(const int32_t *in, int32_t *out, int64_t n, bool write_total, cudaStream_t s) {
+    const int nb = ceil_div(n, kScanTile);
+    if (nb <= 1) {
+        scan_apply_kernel<<<1, kScanThreads, 0, s>>>(in, out, nullptr, n, write_total ? 1 : 0);
+        DCRF_LAUNCHED();
+        return;
+    }
+    DevBuf<int32_t> sums;
+    sums.alloc((size_t)nb + 1, s);
+    scan_reduce_kernel<<<nb, kScanThreads, 0, s>>>(in, sums.p, n);
+    DCRF_LAUNCHED();
+    scan_rec(sums.p, sums.p, nb, false, s);
+    scan_apply_kernel<<<nb, kScanThreads, 0, s>>>(in, out, sums.p, n, write_total ? 1 : 0);
+    DCRF_LAUNCHED();
+}
+
+// ---------------- radix sort ----------------
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortRounds = 16;                                   // 32-key rounds per warp
+constexpr int kSortTile = kSortThreads * kSortRounds;             // 4096 keys per block
+constexpr int kSortWarpChunk = 32 * kSortRounds;                  // 512 contiguous keys per warp
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys,
+                                                                  int32_t *__restrict__ hist,
+                                                                  int64_t n, int shift, int nb) {
+    __shared__ int h[kRadix];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int i = 0; i < kSortRounds; i++) {
+        int64_t idx = base + (int64_t)i * kSortThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
+    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+    const int32_t *__restrict__ hist_scanned, int64_t n, int shift, int nb) {
+    __shared__ int cnt[kSortWarps][kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = lane; i < kRadix; i += 32) cnt[warp][i] = 0;
+    __syncwarp();
+    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * kSortWarpChunk;
+    uint32_t k[kSortRounds];
+    // phase A: per-warp digit counts over the warp's contiguous chunk
+#pragma unroll
+    for (int r = 0; r < kSortRounds; r++) {
+        int64_t idx = wbase + r * 32 + lane;
+        bool valid = idx < n;
+        k[r] = valid ? keys_in[idx] : 0u;
+        int digit = valid ? (int)((k[r] >> shift) & (kRadix - 1)) : (kRadix + lane);
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[warp][digit] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase B: turn counts into start positions: global digit offset of this block + earlier warps
+    {
+        int digit = threadIdx.x;
+        int run = hist_scanned[(int64_t)digit * nb + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            int c = cnt[w][digit];
+            cnt[w][digit] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase C: stable scatter, warp chunk walked in order
+#pragma unroll
+    for (int r = 0; r < kSortRounds; r++) {
+        int64_t idx = wbase + r * 32 + lane;
+        bool valid = idx < n;
+        int digit = valid ? (int)((k[r] >> shift) & (kRadix - 1)) : (kRadix + lane);
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        int rank = __popc(peers & ((1u << lane) - 1));
+        if (valid) {
+            int pos = cnt[warp][digit] + rank;
+            keys_out[pos] = k[r];
+            vals_out[pos] = vals_in[idx];
+        }
+        __syncwarp();
+        if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
+    scan_rec(in, out, n, true, s);
+}
+
+void radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                      int64_t n, int bits, cudaStream_t s) {
+    if (n <= 0) return;
+    int passes = (bits + kRadixBits - 1) / kRadixBits;
+    if (passes < 1) passes = 1;
+    if (passes & 1) passes++;  // even number of passes so that the result lands in *_a
+    const int nb = ceil_div(n, kSortTile);
+    DevBuf<int32_t> hist;
+    hist.alloc((size_t)kRadix * nb + 1, s);
+    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    for (int p = 0; p < passes; p++) {
+        const int shift = p * kRadixBits;
+        radix_hist_kernel<<<nb, kSortThreads, 0, s>>>(ki, hist.p, n, shift, nb);
+        DCRF_LAUNCHED();
+        scan_rec(hist.p, hist.p, (int64_t)kRadix * nb, false, s);
+        radix_scatter_kernel<<<nb, kSortThreads, 0, s>>>(ki, vi, ko, vo, hist.p, n, shift, nb);
+        DCRF_LAUNCHED();
+        uint32_t *t;
+        t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+}
+
+}  // namespace dcrf

@@ -1,0 +1,116 @@
+"""Integer confusion-matrix reduction behind mIoU, on the GPU, summed across GPUs with one NCCL
+all-reduce.
+
+Replaces
+  * chainercv `calc_semantic_segmentation_confusion` + the IoU arithmetic of
+    /root/reference/03b_irn/step/eval_sem_seg.py:41-50 (`iou = diag / (row + col - diag)`,
+    `miou = nanmean(iou)`), and
+  * the per-class intersect / union loops of /root/reference/03a_sec-dsrg/model.py:698-719,736 and
+    /root/reference/03c_hsn/demo.py:185-191,234 (`mIoU = mean(I / (U + 1e-7))`, where the union
+    also counts predicted-k pixels whose GT is an ignored / unlisted value).
+
+Counts are int64 and integer addition is order independent, so the sharded result is bit-identical
+to a single-process NumPy bincount.  PyTorch is used only to own the device buffer and for the
+`torch.distributed` collective (NCCL on GPUs; gloo in the CPU tests, which exercise the host logic
+with host-side counting disabled -- the counting itself always runs in the CUDA kernel).
+"""
+import numpy as np
+
+from . import _lib
+
+
+class ConfusionAccumulator(object):
+    """(C+1, C) int64 device matrix: row = GT class, column = predicted class; row C collects pixels
+    whose GT is outside [0, C) (VOC's 255, chainercv's -1) and is what the IRN convention ignores."""
+
+    def __init__(self, n_classes, device=None):
+        import torch
+
+        self.C = int(n_classes)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.conf = torch.zeros((self.C + 1, self.C), dtype=torch.int64, device=self.device)
+        self.bad = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._lib = _lib.load()
+
+    def _dev_i32(self, x):
+        import torch
+
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32))
+        if x.dtype != torch.int32:
+            x = x.to(torch.int32)
+        return x.to(self.device, non_blocking=False).contiguous().view(-1)
+
+    def update(self, gt, pred):
+        """gt, pred: same-size integer label maps (numpy or torch, host or device)."""
+        import torch
+
+        g, p = self._dev_i32(gt), self._dev_i32(pred)
+        if g.numel() != p.numel():
+            raise ValueError("gt and pred differ in size: %d vs %d" % (g.numel(), p.numel()))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.dcrf_confusion_accumulate(g.data_ptr(), p.data_ptr(), g.numel(), self.C,
+                                                       self.conf.data_ptr(), self.bad.data_ptr(),
+                                                       self.device.index, stream))
+        return self
+
+    def all_reduce(self, group=None):
+        """Sum over all ranks (NCCL over NVLink on GPUs).  No-op without an initialised process group."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.conf, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.bad, op=dist.ReduceOp.SUM, group=group)
+        return self
+
+    def result(self):
+        """(C+1, C) int64 ndarray."""
+        return self.conf.cpu().numpy()
+
+    def bad_predictions(self):
+        return int(self.bad.item())
+
+
+def all_reduce_confusion_host(conf, group=None):
+    """Host-side (gloo) form of the same collective for CPU-only tests of the sharding logic."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(conf, dtype=np.int64))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy()
+
+
+def iou_irn(conf):
+    """IRN / chainercv convention (eval_sem_seg.py:43-50): ignored-GT row dropped,
+    iou = diag / (gt_total + pred_total - diag), miou = nanmean."""
+    c = np.asarray(conf)[:-1].astype(np.int64) if conf.shape[0] == conf.shape[1] + 1 else np.asarray(conf)
+    gtj = c.sum(axis=1)
+    resj = c.sum(axis=0)
+    gtjresj = np.diag(c)
+    denominator = gtj + resj - gtjresj
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = gtjresj / denominator
+    return iou, float(np.nanmean(iou))
+
+
+def iou_sec(conf):
+    """03a / 03c convention (model.py:716-719,736): intersect[k] = #(gt==k & pred==k),
+    union[k] = #(gt==k | pred==k) INCLUDING predicted-k pixels on ignored GT,
+    mIoU = mean(I / (U + 1e-7))."""
+    conf = np.asarray(conf)
+    assert conf.shape[0] == conf.shape[1] + 1, "needs the (C+1, C) matrix with the ignored-GT row"
+    C_ = conf.shape[1]
+    inter = np.diag(conf[:C_]).astype(np.float64)
+    gt_count = conf[:C_].sum(axis=1).astype(np.float64)
+    pred_count = conf.sum(axis=0).astype(np.float64)  # includes the ignored-GT row
+    union = gt_count + pred_count - inter
+    iou = inter / (union + 1e-7)
+    return iou, float(np.mean(iou))
+
+
+def shard_indices(n_items, rank, world_size):
+    """Item i -> rank i mod world_size: the `split_dataset` striding of
+    /root/reference/03b_irn/step/cam_to_ir_label.py:114-117."""
+    return list(range(rank, n_items, world_size))

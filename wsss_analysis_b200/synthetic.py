@@ -1,0 +1,89 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names.  NumPy/SciPy only.
+
+No dataset or checkpoint is available offline, so tests and bench.py use these: "natural-like" images
+(smooth colour field + noise; lattice sizes close to real photographs), "iid" images (worst case for
+the bilateral lattice), "histo" images (pinkish-white background with darker blobs) and unaries
+drawn as -log softmax(3 * N(0,1)).
+"""
+import numpy as np
+
+
+def natural_image(H, W, seed=0):
+    from scipy import ndimage
+
+    rng = np.random.default_rng(seed)
+    gh, gw = H // 32 + 2, W // 32 + 2
+    grid = rng.uniform(0, 255, (gh, gw, 3))
+    up = ndimage.zoom(grid, (H / gh, W / gw, 1), order=3, mode="nearest", grid_mode=True)
+    up = up[:H, :W]
+    if up.shape[0] < H or up.shape[1] < W:
+        up = np.pad(up, ((0, H - up.shape[0]), (0, W - up.shape[1]), (0, 0)), mode="edge")
+    img = up + rng.normal(0, 8, (H, W, 3))
+    return np.ascontiguousarray(np.clip(img, 0, 255).astype(np.uint8))
+
+
+def iid_image(H, W, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+
+def histo_image(H, W, seed=0, n_blobs=40):
+    rng = np.random.default_rng(seed)
+    img = np.full((H, W, 3), 244.0) + rng.normal(0, 2.0, (H, W, 3))
+    img[..., 1] -= 6
+    yy, xx = np.mgrid[0:H, 0:W]
+    for _ in range(n_blobs):
+        cy, cx = rng.uniform(0, H), rng.uniform(0, W)
+        r = rng.uniform(0.02, 0.12) * min(H, W)
+        col = rng.uniform(60, 200, 3) * np.array([1.0, 0.6, 1.0])
+        m = np.exp(-(((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r)))
+        img = img * (1 - m[..., None]) + col * m[..., None]
+    img += rng.normal(0, 4.0, (H, W, 3))
+    return np.ascontiguousarray(np.clip(img, 0, 255).astype(np.uint8))
+
+
+def random_unary(L, N, seed=0, sharp=3.0):
+    """(L, N) float32 energies = -log softmax(sharp * N(0,1))."""
+    rng = np.random.default_rng(seed + 7919)
+    z = rng.standard_normal((L, N)) * sharp
+    z -= z.max(axis=0, keepdims=True)
+    lse = np.log(np.exp(z).sum(axis=0, keepdims=True))
+    return np.ascontiguousarray((-(z - lse)).astype(np.float32))
+
+
+def blob_probs(C, H, W, seed=0, n_active=None):
+    """(C, H, W) float64 class probabilities with smooth spatial structure; inactive classes are 0
+    everywhere (exercises the class sub-selection of 03c_hsn/utilities.py:425)."""
+    from scipy import ndimage
+
+    rng = np.random.default_rng(seed + 104729)
+    active = np.arange(C) if n_active is None else np.sort(rng.choice(C, n_active, replace=False))
+    z = np.zeros((C, H, W))
+    for c in active:
+        z[c] = ndimage.gaussian_filter(rng.standard_normal((H, W)), sigma=max(2.0, min(H, W) / 16.0)) * 25.0
+    e = np.zeros_like(z)
+    e[active] = np.exp(z[active] - z[active].max(axis=0, keepdims=True))
+    e /= e.sum(axis=0, keepdims=True)
+    return e
+
+
+def voc_like_sizes(n, seed=0):
+    """(W, H) pairs drawn from common VOC2012 image sizes."""
+    rng = np.random.default_rng(seed + 15485863)
+    choices = [(500, 375), (375, 500), (500, 333), (500, 500), (334, 500), (500, 334), (500, 374), (480, 360)]
+    idx = rng.integers(0, len(choices), n)
+    return [choices[i] for i in idx]
+
+
+def gt_map(H, W, C, seed=0, ignore=255, border=4):
+    """int32 GT label map with blobs and an `ignore` border (VOC-style 255)."""
+    from scipy import ndimage
+
+    rng = np.random.default_rng(seed + 32452843)
+    z = np.stack([ndimage.gaussian_filter(rng.standard_normal((H, W)), sigma=min(H, W) / 10.0) for _ in range(C)])
+    gt = z.argmax(axis=0).astype(np.int32)
+    gt[:border] = ignore
+    gt[-border:] = ignore
+    gt[:, :border] = ignore
+    gt[:, -border:] = ignore
+    return gt
