@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- DenseCRF mean-field throughput on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic VOC2012-shaped images
+(500x375 RGB, 21 labels, 10 mean-field iterations, Gaussian sxy=3 compat=3, bilateral sxy=80
+srgb=13 compat=10 -- /root/reference/03a_sec-dsrg/SEC.py:20): for every image the two permutohedral
+lattices are built (a new image means a new lattice) and 10 iterations are run.
+`value`  : Mpix*iter/s with unaries and images already resident in HBM (device pointers in, device out)
+`e2e`    : the same batch through the same C-ABI calls with HOST (pinned) buffers: H2D of unaries and
+           images and D2H of the marginals Q are inside the timed region.
+One process per GPU; images shard over ranks with no data-path collective ("weak" scaling: the
+per-GPU batch is fixed); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG, L_LAB, N_ITER = 500, 375, 21, 10
+G_SXY, G_COMPAT, B_SXY, B_SRGB, B_COMPAT = 3.0, 3.0, 80.0, 13.0, 10.0
+METRIC, UNIT = "densecrf_mpix_iter_per_s", "Mpix*iter/s"
+N_DISTINCT = 4  # distinct synthetic images generated on the host, tiled up to the batch size
+
+
+def config_dict(batch, impl):
+    return {
+        "workload": "voc2012_shaped_batch: %d images/GPU/step of %dx%d RGB, %d labels, %d iterations, "
+                    "gaussian sxy=%g compat=%g + bilateral sxy=%g srgb=%g compat=%g, lattice build included"
+                    % (batch, W_IMG, H_IMG, L_LAB, N_ITER, G_SXY, G_COMPAT, B_SXY, B_SRGB, B_COMPAT),
+        "images_per_gpu_per_step": batch,
+        "image": "natural-like synthetic (smooth colour field + N(0,8) noise), seeds 0..%d tiled" % (N_DISTINCT - 1),
+        "l2_policy": "inputs larger than L2 (unaries alone are %.0f MB per step per GPU)"
+                     % (batch * L_LAB * W_IMG * H_IMG * 4 / 1e6),
+        "impl": impl,
+    }
+
+
+def make_inputs(batch):
+    from wsss_analysis_b200 import synthetic as S
+
+    imgs = [S.natural_image(H_IMG, W_IMG, s) for s in range(N_DISTINCT)]
+    unaries = [S.random_unary(L_LAB, W_IMG * H_IMG, s) for s in range(N_DISTINCT)]
+    return [imgs[i % N_DISTINCT] for i in range(batch)], [unaries[i % N_DISTINCT] for i in range(batch)]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle restatement of pydensecrf (pydensecrf itself cannot be installed
+# here: SURVEY.md section 0.2), one image per thread on all host cores.
+# ------------------------------------------------------------------------------------------------
+def cpu_one_image(args):
+    from oracle import oracle as O
+
+    img, U = args
+    d = O.DenseCRF2D(W_IMG, H_IMG, L_LAB)
+    d.setUnaryEnergy(U)
+    d.addPairwiseGaussian(sxy=G_SXY, compat=G_COMPAT)
+    d.addPairwiseBilateral(sxy=B_SXY, srgb=B_SRGB, rgbim=img, compat=B_COMPAT)
+    return d.inference(N_ITER)
+
+
+def cpu_sample(n_images, threads):
+    """Wall time of `n_images` VOC-shaped CRFs over `threads` host threads (ctypes drops the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+
+    O.lib()
+    imgs, unaries = make_inputs(min(n_images, N_DISTINCT))
+    work = [(imgs[i % len(imgs)], unaries[i % len(unaries)]) for i in range(n_images)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(cpu_one_image, work))
+    return time.perf_counter() - t0
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    n_images = threads  # one image per thread per step: a bounded sample of the batch workload
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_sample(min(n_images, threads), threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(n_images, threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_images * W_IMG * H_IMG * N_ITER / dt / 1e6
+    sample = "%d VOC-shaped images per step (one per host thread), %d steps" % (n_images, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(n_images, "oracle port of pydensecrf on host cores"),
+        "images_per_s": args.steps * n_images / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+            # nvidia-smi's start-up stalls driver calls of other processes for ~100 ms: wait for
+            # its first sample so that the stall is outside the timed region
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 10.0:
+                time.sleep(0.05)
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(cls, d, N, L, M, n_terms_info=None):
+    """Algorithmic bytes of ONE launch (DESIGN.md section 'Roofline accounting'); float32 values,
+    int32 ids, L real labels (padding lanes are not counted)."""
+    if cls == "splat":   # Q read + norm + (pixel id, weight) per entry + row starts + lattice write
+        return 4 * L * N + 4 * N + 8 * (d + 1) * N + 4 * M + 4 * L * M
+    if cls == "blur":    # lattice read + write + two neighbour ids
+        return 8 * L * M + 8 * M
+    if cls == "slice":   # unary read + Q write + per term: (offset, weight) per entry + lattice read + norm
+        b = 8 * L * N
+        for (dk, Mk) in n_terms_info:
+            b += 8 * (dk + 1) * N + 4 * L * Mk + 4 * N
+        return b
+    raise KeyError(cls)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from wsss_analysis_b200 import densecrf as G
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    N = W_IMG * H_IMG
+    imgs, unaries = make_inputs(B)
+    sizes = [(W_IMG, H_IMG)] * B
+    # host (pinned) and device copies of the step's inputs / outputs
+    U_host = torch.from_numpy(np.concatenate([u.ravel() for u in unaries])).pin_memory()
+    I_host = torch.from_numpy(np.concatenate([im.ravel() for im in imgs])).pin_memory()
+    Q_host = torch.empty(B * L_LAB * N, dtype=torch.float32).pin_memory()
+    U_dev, I_dev = U_host.to(dev), I_host.to(dev)
+    Q_dev = torch.empty(B * L_LAB * N, dtype=torch.float32, device=dev)
+    # a real (non-default) stream: the library launches on it and the CUDA events below bracket it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
+
+    prof = {"splat": {}, "blur": {}, "slice": {}}
+    lattice_M = {}
+
+    def step(device_resident, profile=False):
+        crf = G.DenseCRFBatch(sizes, L_LAB, device=local, stream=stream)
+        if profile:
+            crf.profile_enable(True)
+        if device_resident:
+            crf.setUnaryEnergy(U_dev)
+            crf.addPairwiseGaussian(sxy=G_SXY, compat=G_COMPAT)
+            crf.addPairwiseBilateral(sxy=B_SXY, srgb=B_SRGB, rgbim=I_dev, compat=B_COMPAT)
+            crf.inference_device(N_ITER, out=Q_dev)
+        else:
+            crf.setUnaryEnergy(U_host.numpy())
+            crf.addPairwiseGaussian(sxy=G_SXY, compat=G_COMPAT)
+            crf.addPairwiseBilateral(sxy=B_SXY, srgb=B_SRGB, rgbim=I_host.numpy(), compat=B_COMPAT)
+            crf.inference(N_ITER, out=Q_host.numpy())
+        if profile:
+            for k in range(2):
+                d, M, _ = crf.lattice_info(k)
+                lattice_M[d] = M
+            for cls, cid in (("splat", 0), ("blur", 1), ("slice", 2)):
+                for tag in ((2, 5) if cls != "slice" else (2,)):
+                    ms, n = crf.profile_read(cid, tag)
+                    a = prof[cls].setdefault(tag, [0.0, 0])
+                    a[0] += ms
+                    a[1] += n
+        crf.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(device_resident, steps, profile):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = G.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            step(device_resident, profile)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = G.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(True, args.steps, True)
+    ms_e2e, _ = timed(False, args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_pix_iter = world * B * N * N_ITER * args.steps
+    value = total_pix_iter / (ms_dev * 1e-3) / 1e6
+    e2e_value = total_pix_iter / (ms_e2e * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel class (largest share of device time in the timed region)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    Ntot = B * N
+    kernels = []
+    for cls in ("splat", "blur", "slice"):
+        for tag, (ms, n) in prof[cls].items():
+            if n == 0:
+                continue
+            if cls == "slice":
+                info = [(d, lattice_M[d]) for d in sorted(lattice_M)]
+                by = algorithmic_bytes("slice", None, Ntot, L_LAB, None, info)
+                name = "slice_softmax_kernel (fused %d terms)" % tag
+            else:
+                by = algorithmic_bytes(cls, tag, Ntot, L_LAB, lattice_M[tag])
+                name = "%s_kernel d=%d" % (cls, tag)
+            kernels.append({"kernel": name, "launches": n, "total_ms": ms, "avg_us": ms / n * 1e3,
+                            "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms / n * 1e-3) / 1e9})
+    kernels.sort(key=lambda k: -k["total_ms"])
+    top = kernels[0]
+    kernel_ms = sum(k["total_ms"] for k in kernels)
+    roofline = {
+        "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        "frac": top["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "share_of_step": top["total_ms"] / ms_dev,
+        "per_kernel": [{"kernel": k["kernel"], "launches": k["launches"], "avg_us": round(k["avg_us"], 2),
+                        "achieved_gbs": round(k["achieved_gbs"], 1), "frac": round(k["achieved_gbs"] / peak, 4),
+                        "share_of_step": round(k["total_ms"] / ms_dev, 4)} for k in kernels],
+        "iteration_kernels_share_of_step": kernel_ms / ms_dev,
+    }
+
+    cpu = None
+    if world == 1:
+        threads = host_threads()
+        n_img = threads
+        dt = cpu_sample(n_img, threads)
+        cpu = {"value": n_img * N * N_ITER / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d VOC-shaped images, one per host thread, oracle restatement of pydensecrf "
+                         "(%.2f s wall)" % (n_img, dt),
+               "images_per_s": n_img / dt}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(B, "wsss_analysis_b200 (libdcrf_b200.so, sm_100a)"),
+        "images_per_s": world * B * args.steps / (ms_dev * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "images_per_s": world * B * args.steps / (ms_e2e * 1e-3),
+                "h2d_bytes_per_step": int(U_host.numel() * 4 + I_host.numel()),
+                "d2h_bytes_per_step": int(Q_host.numel() * 4),
+                "api": "DenseCRFBatch.setUnaryEnergy/addPairwiseGaussian/addPairwiseBilateral/inference "
+                       "with pinned host buffers (dcrf_set_unary / dcrf_add_pairwise_* / dcrf_inference, on_device=0)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

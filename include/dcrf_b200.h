@@ -133,6 +133,17 @@ int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t
  * compat) to host values (L, N) -> (L, N); batch-of-one only.  Test hook. */
 int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int value_size);
 
+/* ---- measurement hooks (bench.py's roofline object) ------------------------------------------ */
+
+/* Kernel classes timed with CUDA events recorded on the handle's stream around every launch. */
+enum { DCRF_K_SPLAT = 0, DCRF_K_BLUR = 1, DCRF_K_SLICE = 2 };
+int dcrf_profile_enable(dcrf_t *h, int enable);
+/* Synchronises the stream, then sums the recorded launches of `kernel_class` whose tag equals `tag`
+ * (tag = lattice dimension d for splat / blur, number of fused pairwise terms for slice; -1 = any).
+ * reset != 0 clears the records of every class afterwards. */
+int dcrf_profile_read(dcrf_t *h, int kernel_class, int tag, double *total_ms, int64_t *launches,
+                      int reset);
+
 /* ---- evaluation reduction (the integer collective behind mIoU) --------------------------------- */
 
 /* Replaces chainercv `calc_semantic_segmentation_confusion` as called at

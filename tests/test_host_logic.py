@@ -1,0 +1,122 @@
+"""CPU: host-side mirrors of the reference interface (NumPy glue, metric conventions, sharding)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from wsss_analysis_b200 import evaluation as E
+from wsss_analysis_b200 import synthetic as S
+from wsss_analysis_b200 import utils, wsss
+
+
+def test_unary_from_softmax_matches_restatement():
+    rng = np.random.default_rng(0)
+    sm = rng.random((5, 7, 9))
+    sm /= sm.sum(0)
+    sm[0, 0, 0] = 0.0  # exercises the clip
+    for kw in ({}, {"scale": 0.7}, {"clip": None, "scale": 0.5}):
+        a, b = utils.unary_from_softmax(sm, **kw), O.unary_from_softmax(sm, **kw)
+        assert a.dtype == np.float32 and a.shape == (5, 63) and np.array_equal(a, b)
+    assert utils.unary_from_softmax(sm)[0, 0] == np.float32(-np.log(1e-5))
+
+
+def test_unary_from_labels_matches_restatement():
+    rng = np.random.default_rng(1)
+    lab = rng.integers(0, 4, (6, 5))
+    for zu in (True, False):
+        a, b = utils.unary_from_labels(lab, 4, 0.7, zero_unsure=zu), O.unary_from_labels(lab, 4, 0.7, zero_unsure=zu)
+        assert a.dtype == np.float32 and np.array_equal(a, b)
+    U = utils.unary_from_labels(lab, 4, 0.7, zero_unsure=False)
+    p = lab.ravel()
+    assert np.allclose(U[p, np.arange(p.size)], -np.log(0.7))
+    assert np.allclose(np.delete(U[:, 0], p[0]), -np.log(0.3 / 3))
+
+
+def test_create_pairwise_features_match_2d_kernels():
+    H, W = 5, 7
+    img = S.natural_image(H, W, 0)
+    fg = utils.create_pairwise_gaussian((3, 2), (H, W))
+    assert fg.shape == (2, H * W)
+    ys, xs = np.mgrid[0:H, 0:W]
+    assert np.allclose(fg[0], ys.ravel() / 3) and np.allclose(fg[1], xs.ravel() / 2)
+    fb = utils.create_pairwise_bilateral((3, 2), (13, 13, 13), img, chdim=2)
+    assert fb.shape == (5, H * W) and np.allclose(fb[2], img[..., 0].ravel() / 13)
+
+
+def test_active_class_grouping_follows_dcrf_process():
+    probs = S.blob_probs(6, 8, 8, seed=0, n_active=3)
+    act = wsss._active_classes(probs)
+    assert len(act) == 3 and (probs[act].sum((1, 2)) > 0).all()
+    assert wsss._group_by([3, 2, 3, 0, 2]) == {3: [0, 2], 2: [1, 4], 0: [3]}
+
+
+def test_unary_from_featmap_is_softmax_neglog():
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal((4, 5, 3)).astype(np.float32)
+    U = wsss._unary_from_featmap(f, use_log=True)
+    assert U.shape == (3, 20) and U.flags.c_contiguous and U.dtype == np.float32
+    p = np.exp(f) / np.exp(f).sum(2, keepdims=True)
+    assert np.allclose(U, -np.log(p).reshape(20, 3).T, atol=1e-5)
+
+
+def _reference_iou_irn(confusion):
+    # literal restatement of 03b_irn/step/eval_sem_seg.py:43-50
+    gtj = confusion.sum(axis=1)
+    resj = confusion.sum(axis=0)
+    gtjresj = np.diag(confusion)
+    denominator = gtj + resj - gtjresj
+    iou = gtjresj / denominator
+    return iou, np.nanmean(iou)
+
+
+def _reference_iou_sec(gt, pred, C_):
+    # literal restatement of 03a_sec-dsrg/model.py:698-719,736 (VOC branch)
+    intersect, union = np.zeros(C_), np.zeros(C_)
+    for k in range(C_):
+        gt_mask, pred_mask = gt == k, pred == k
+        intersect[k] += np.sum(gt_mask & pred_mask)
+        union[k] += np.sum(gt_mask | pred_mask)
+    return intersect / (union + 1e-7), np.mean(intersect / (union + 1e-7))
+
+
+def test_miou_conventions():
+    rng = np.random.default_rng(3)
+    C_ = 7
+    gt = rng.integers(0, C_, 4000).astype(np.int32)
+    gt[::13] = 255
+    pred = rng.integers(0, C_ - 1, gt.size).astype(np.int32)  # class C-1 never predicted
+    conf = O.confusion(gt, pred, C_)
+    iou, miou = E.iou_irn(conf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        riou, rmiou = _reference_iou_irn(conf[:C_])
+    assert np.array_equal(np.nan_to_num(iou, nan=-1), np.nan_to_num(riou, nan=-1)) and miou == rmiou
+    iou2, miou2 = E.iou_sec(conf)
+    riou2, rmiou2 = _reference_iou_sec(gt, pred, C_)
+    assert np.array_equal(iou2, riou2) and miou2 == rmiou2
+
+
+def test_shard_indices_stride():
+    assert E.shard_indices(10, 1, 4) == [1, 5, 9]
+    allidx = sorted(sum((E.shard_indices(1449, r, 8) for r in range(8)), []))
+    assert allidx == list(range(1449))
+
+
+def test_synthetic_inputs_are_seeded():
+    assert np.array_equal(S.natural_image(20, 30, 5), S.natural_image(20, 30, 5))
+    assert not np.array_equal(S.natural_image(20, 30, 5), S.natural_image(20, 30, 6))
+    U = S.random_unary(4, 50, 0)
+    assert U.dtype == np.float32 and np.allclose(np.exp(-U).sum(0), 1, atol=1e-5)
+    gt = S.gt_map(30, 40, 5, 0)
+    assert gt.dtype == np.int32 and set(np.unique(gt)) <= set(range(5)) | {255}
+
+
+def test_bench_algorithmic_bytes_formula():
+    import bench
+
+    N, L, Mg, Mb = 1000, 21, 130, 640
+    per_iter = (bench.algorithmic_bytes("splat", 2, N, L, Mg) + bench.algorithmic_bytes("splat", 5, N, L, Mb)
+                + 3 * bench.algorithmic_bytes("blur", 2, N, L, Mg) + 6 * bench.algorithmic_bytes("blur", 5, N, L, Mb)
+                + bench.algorithmic_bytes("slice", None, N, L, None, [(2, Mg), (5, Mb)]))
+    # SURVEY.md section 8d formula + one extra Q read (two splat launches) + norms and row starts
+    survey = 12 * L * N + sum(16 * (d + 1) * N + 8 * L * M + (d + 1) * (8 * L * M + 8 * M) for d, M in ((2, Mg), (5, Mb)))
+    extra = 4 * L * N + 4 * 4 * N + 4 * (Mg + Mb)
+    assert per_iter == survey + extra

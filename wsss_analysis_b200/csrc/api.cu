@@ -13,6 +13,7 @@ namespace dcrf {
 
 std::atomic<int64_t> g_launches{0};
 static thread_local std::string t_error;
+thread_local Profiler *t_prof = nullptr;
 void set_error(const std::string &msg) { t_error = msg; }
 
 struct Pairwise {
@@ -40,6 +41,7 @@ struct dcrf_handle {
     DevBuf<float> unary, Q;
     bool unary_set = false, q_valid = false;
     std::vector<std::unique_ptr<Pairwise>> pw;
+    Profiler prof;
 };
 
 namespace {
@@ -53,6 +55,10 @@ struct DeviceGuard {
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
     }
+};
+struct ProfGuard {
+    explicit ProfGuard(dcrf_handle *h) { t_prof = &h->prof; }
+    ~ProfGuard() { t_prof = nullptr; }
 };
 
 template <typename F>
@@ -404,6 +410,7 @@ int dcrf_inference(dcrf_t *h, int n_iter, float *Q_out, int on_device) {
     return guarded([&] {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         run_inference(h, n_iter);
         emit_q(h, Q_out, on_device);
     });
@@ -413,6 +420,7 @@ int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device) {
     return guarded([&] {
         DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         run_inference(h, n_iter);
         const int64_t N = h->geom.Ntot;
         if (on_device) {
@@ -440,6 +448,7 @@ int dcrf_step_inference(dcrf_t *h) {
     return guarded([&] {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         step_inference(h);
     });
 }
@@ -489,6 +498,36 @@ int dcrf_kl_divergence(dcrf_t *h, double *kl_out) {
         launch_kl(h->Q.p, h->unary.p, ptrs, (int)h->pw.size(), Ntot, h->L, h->Lp, d_out.p, s);
         DCRF_CUDA(cudaMemcpyAsync(kl_out, d_out.p, sizeof(double), cudaMemcpyDeviceToHost, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int dcrf_profile_enable(dcrf_t *h, int enable) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        h->prof.on = enable != 0;
+    });
+}
+
+int dcrf_profile_read(dcrf_t *h, int kernel_class, int tag, double *total_ms, int64_t *launches, int reset) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DeviceGuard guard(h->device);
+        DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        double ms = 0;
+        int64_t n = 0;
+        for (auto &r : h->prof.recs) {
+            if (r.cls != kernel_class || (tag >= 0 && r.tag != tag)) continue;
+            float t = 0;
+            DCRF_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+            ms += t;
+            n++;
+        }
+        if (total_ms) *total_ms = ms;
+        if (launches) *launches = n;
+        if (reset) {
+            for (auto &r : h->prof.recs) { h->prof.pool.push_back(r.a); h->prof.pool.push_back(r.b); }
+            h->prof.recs.clear();
+        }
     });
 }
 

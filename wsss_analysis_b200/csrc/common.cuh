@@ -73,6 +73,42 @@ struct DevBuf {
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// per-kernel-class device timing with CUDA events on the launching stream (bench.py's roofline)
+// ---------------------------------------------------------------------------------------------
+struct Profiler {
+    struct Rec { int cls, tag; cudaEvent_t a, b; };
+    bool on = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        cudaEvent_t e;
+        if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+        DCRF_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    ~Profiler() {
+        for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+extern thread_local Profiler *t_prof;  // set by the API entry points while a handle is being driven
+struct ProfScope {
+    Profiler *p;
+    cudaStream_t s;
+    cudaEvent_t b = nullptr;
+    ProfScope(int cls, int tag, cudaStream_t stream) : p(t_prof), s(stream) {
+        if (!p || !p->on) { p = nullptr; return; }
+        cudaEvent_t a = p->get();
+        b = p->get();
+        DCRF_CUDA(cudaEventRecord(a, s));
+        p->recs.push_back({cls, tag, a, b});
+    }
+    ~ProfScope() {
+        if (p) cudaEventRecord(b, s);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // lattice construction (lattice_build.cu)
 // ---------------------------------------------------------------------------------------------
 struct FeatureSpec {

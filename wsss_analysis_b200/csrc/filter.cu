@@ -435,6 +435,7 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
     if (lat.M == 0) return;
     const int g = Lp / 4;
     const int nb = ceil_div(lat.M, rows_per_block(g));
+    ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     DCRF_DISPATCH_G(g, {
         if (norm_pre)
             splat_kernel<G, true><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_pix.p, lat.csr_w.p, Q,
@@ -452,6 +453,7 @@ void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int 
     const int g = Lp / 4;
     const int nb = ceil_div(lat.M, rows_per_block(g));
     const int2 *nbr = lat.neigh.p + (int64_t)axis * lat.M;
+    ProfScope prof(DCRF_K_BLUR, lat.d, s);
     DCRF_DISPATCH_G(g, {
         if (seq) blur_kernel<G, true><<<nb, kThreads, 0, s>>>(nbr, in, out, lat.M, g);
         else blur_kernel<G, false><<<nb, kThreads, 0, s>>>(nbr, in, out, lat.M, g);
@@ -464,6 +466,7 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
     if (Ntot == 0) return;
     const int g = Lp / 4;
     const int nb = ceil_div(Ntot, rows_per_block(g));
+    ProfScope prof(DCRF_K_SLICE, a.n_terms, s);
     DCRF_DISPATCH_G(g, { slice_softmax_kernel<G><<<nb, kThreads, 0, s>>>(a, unary, Q, Ntot, L, g); });
     DCRF_LAUNCHED();
 }

@@ -370,11 +370,6 @@ __global__ void __launch_bounds__(kThreads) csr_finalize_kernel(
     if (s == E - 1) csr_start[M] = (int32_t)E;
 }
 
-__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) p[i] = v;
-}
 
 template <int D>
 void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {

@@ -222,6 +222,17 @@ class _Model(object):
         del keep
         return kl.value
 
+    # -- measurement hooks (bench.py) --
+    def profile_enable(self, on=True):
+        _lib.check(self._lib.dcrf_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, kernel_class, tag=-1, reset=False):
+        """-> (total device ms, launches) of one kernel class since the last reset."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self._lib.dcrf_profile_read(self._h, int(kernel_class), int(tag), C.byref(ms), C.byref(n),
+                                               1 if reset else 0))
+        return ms.value, n.value
+
     # -- introspection (tests) --
     def num_pairwise(self):
         n = C.c_int(0)
@@ -382,9 +393,12 @@ class DenseCRFBatch(_Model):
             o += n
         return out
 
-    def inference(self, niter):
-        """-> list of (L, N_b) float32 arrays (views of one flat host buffer)."""
-        flat = np.empty(self._Ntot * self._L, np.float32)
+    def inference(self, niter, out=None):
+        """-> list of (L, N_b) float32 arrays (views of one flat host buffer; `out` may supply it,
+        e.g. a numpy view of pinned memory)."""
+        flat = np.empty(self._Ntot * self._L, np.float32) if out is None else out
+        assert flat.dtype == np.float32 and flat.size == self._Ntot * self._L and flat.flags.c_contiguous
+        flat = flat.reshape(-1)
         _lib.check(self._lib.dcrf_inference(self._h, int(niter), flat.ctypes.data, 0))
         return self._split(flat, self._L, lambda b: (self._L, int(self._npix[b])))
 

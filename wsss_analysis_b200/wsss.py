@@ -1,0 +1,151 @@
+"""The reference's CRF call-site helpers, re-hosted on the batched B200 engine.
+
+Each function keeps the name, argument meaning and return layout of the helper it replaces so the
+wsss-analysis call sites switch over with an import change only:
+
+  dcrf_process          /root/reference/03c_hsn/utilities.py:399-445          (in tree)
+  crf_inference         03a_sec-dsrg `lib/crf.py` -- file missing from the tree; signature from its
+                        call sites SEC.py:275, DSRG.py:328, model.py:689,693
+  sec_crf_layer         the `crf` py_func closure of SEC.py:270-280 / DSRG.py:323-332
+  crf_inference_label   03b_irn `misc/imutils.py` -- file missing; call sites
+                        step/cam_to_ir_label.py:35,47,52,67
+
+Where the reference loops over images serially, these run every image of the call in ONE batched
+handle (all kernels cover the whole batch).  Host-side NumPy here is only shape / dtype glue and the
+unary construction the reference also does in NumPy; the CRF itself has no CPU path.
+"""
+import numpy as np
+
+from .densecrf import DenseCRFBatch
+from .utils import unary_from_labels, unary_from_softmax
+
+__all__ = ["dcrf_process", "crf_inference", "crf_inference_batch", "sec_crf_layer", "crf_inference_label",
+           "crf_inference_label_batch", "IRN_CRF_CONFIG"]
+
+# [EXT] defaults of jiwoon-ahn/irn `crf_inference_label` (last row)
+IRN_CRF_CONFIG = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 50, "bi_srgb": 5, "bi_compat": 10, "iterations": 10}
+
+
+def _active_classes(probs_img):
+    """`np.where(np.sum(np.sum(probs[i], axis=1), axis=1) > 0)` of utilities.py:425."""
+    return np.where(np.sum(np.sum(probs_img, axis=1), axis=1) > 0)[0]
+
+
+def _group_by(keys):
+    """indices grouped by key, groups in order of first appearance, indices ascending."""
+    groups = {}
+    for i, k in enumerate(keys):
+        groups.setdefault(k, []).append(i)
+    return groups
+
+
+def dcrf_process(probs, images, config, device=None):
+    """Drop-in for `dcrf_process(probs, images, config)` (03c_hsn/utilities.py:399-445).
+
+    probs  (B, C, H, W) class probabilities; images (B, H, W, 3) any dtype (cast with np.uint8 like
+    the reference); config = (gauss_sxy, gauss_compat, bilat_sxy, bilat_srgb, bilat_compat, n_infer)
+    with n_infer possibly float-valued.  Returns (B, H, W) int64 argmax over the C classes of the
+    per-image CRF marginals scattered back to their class slots (inactive classes stay 0).
+
+    Images are grouped by their number of active classes and each group runs as one batch."""
+    gauss_sxy, gauss_compat, bilat_sxy, bilat_srgb, bilat_compat, n_infer = config
+    probs = np.asarray(probs)
+    num_input_images, num_classes = probs.shape[0], probs.shape[1]
+    size = images.shape[1:3]
+    H, W = int(size[0]), int(size[1])
+    crf = np.zeros((num_input_images, num_classes, H, W))
+    active = [_active_classes(probs[i]) for i in range(num_input_images)]
+    for n_act, idx in _group_by([len(a) for a in active]).items():
+        if n_act == 0:
+            continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0
+        d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
+        d.setUnaryEnergy([np.ascontiguousarray(unary_from_softmax(probs[i, active[i]])) for i in idx])
+        d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
+        d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=[np.uint8(images[i]) for i in idx],
+                               compat=bilat_compat)
+        Q = d.inference(n_infer)
+        d.close()
+        for j, i in enumerate(idx):
+            crf[i, active[i]] = Q[j].reshape((n_act, H, W))
+    return np.argmax(crf, axis=1)
+
+
+def _unary_from_featmap(feat, use_log):
+    """[EXT] unary of SEC's crf_inference: softmax over the class axis then -log (use_log=True), or
+    -log of the given probabilities; returned as C-contiguous (C, H*W) float32."""
+    feat = np.asarray(feat, dtype=np.float32)
+    C_ = feat.shape[-1]
+    if use_log:
+        feat = np.exp(feat - np.max(feat, axis=2, keepdims=True))
+        feat /= np.sum(feat, axis=2, keepdims=True)
+        unary = -np.log(feat)
+    else:
+        unary = -np.log(feat)
+    unary = np.reshape(unary, (-1, C_))
+    unary = np.swapaxes(unary, 0, 1)
+    return np.copy(unary, order="C").astype(np.float32, copy=False)
+
+
+def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, device=None):
+    """Batched `crf_inference`: imgs list of (H_b, W_b, 3) uint8, featmaps list of (H_b, W_b, C).
+    Returns a list of (H_b, W_b, C) float32 marginals."""
+    sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
+    d = DenseCRFBatch(sizes, num_classes, device=device)
+    d.setUnaryEnergy([_unary_from_featmap(f, use_log) for f in featmaps])
+    d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
+    d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
+                           rgbim=[np.ascontiguousarray(im, dtype=np.uint8) for im in imgs],
+                           compat=crf_config["bi_compat"])
+    Q = d.inference(crf_config["iterations"])
+    d.close()
+    return [np.transpose(q.reshape((num_classes, h, w)), (1, 2, 0)) for q, (w, h) in zip(Q, sizes)]
+
+
+def crf_inference(img, crf_config, num_classes, featmap, use_log=True, device=None):
+    """Drop-in for SEC/DSRG's `crf_inference(img, crf_config, num_classes, featmap, use_log=True)`
+    (call sites 03a_sec-dsrg/SEC.py:275, model.py:689-693): (H, W, 3) uint8 image + (H, W, C) feature
+    map -> (H, W, C) float32 marginals."""
+    return crf_inference_batch([img], crf_config, num_classes, [featmap], use_log, device)[0]
+
+
+def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, device=None):
+    """The `crf` closure run through tf.py_func in SEC.py:270-280 / DSRG.py:323-332, whole batch in
+    one handle: featemap (B, h, w, C) float32, image (B, h, w, 3) float -> uint8;
+    returns log of the clamped (>= min_prob), renormalised marginals, (B, h, w, C) float32."""
+    featemap = np.asarray(featemap)
+    batch_size = featemap.shape[0]
+    image = np.asarray(image).astype(np.uint8)
+    ret = np.zeros(featemap.shape, dtype=np.float32)
+    out = crf_inference_batch([image[i] for i in range(batch_size)], crf_config, num_classes,
+                              [featemap[i] for i in range(batch_size)], use_log=True, device=device)
+    for i in range(batch_size):
+        ret[i, :, :, :] = out[i]
+    ret[ret < min_prob] = min_prob
+    ret /= np.sum(ret, axis=3, keepdims=True)
+    ret = np.log(ret)
+    return ret.astype(np.float32)
+
+
+def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None):
+    """Batched `crf_inference_label`: returns a list of (H_b, W_b) int label maps."""
+    cfg = dict(IRN_CRF_CONFIG if crf_config is None else crf_config)
+    sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
+    d = DenseCRFBatch(sizes, n_labels, device=device)
+    d.setUnaryEnergy([unary_from_labels(np.asarray(lab), n_labels, gt_prob=gt_prob, zero_unsure=False)
+                      for lab in labels])
+    d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
+    # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
+    d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
+                           rgbim=[np.ascontiguousarray(np.asarray(im).astype(np.uint8)) for im in imgs],
+                           compat=cfg["bi_compat"])
+    out = d.map(t)
+    d.close()
+    return [o.astype(np.int64) for o in out]
+
+
+def crf_inference_label(img, labels, dataset=None, t=10, n_labels=21, gt_prob=0.7, device=None):
+    """Drop-in for `imutils.crf_inference_label(img, labels, dataset, n_labels=...)`
+    (03b_irn/step/cam_to_ir_label.py:35,47,52,67).  `dataset` is this fork's extra positional
+    argument; its effect in the missing wrapper is unknown and it is ignored here."""
+    del dataset
+    return crf_inference_label_batch([img], [labels], n_labels=n_labels, t=t, gt_prob=gt_prob, device=device)[0]
