@@ -76,6 +76,14 @@ int dcrf_create_batch(int n_images, const int *w, const int *h, int n_labels, in
                       void *stream, dcrf_t **out);
 
 void dcrf_destroy(dcrf_t *h);
+
+/* Options.  DCRF_OPT_EXACT_ARITHMETIC = 1 makes the per-iteration kernels use the specification's
+ * float association literally (separately rounded multiply/add, libm-accurate exp and division, no
+ * folding of the normalisation into the splat weights): lattice values then match a sequential CPU
+ * evaluation bit for bit, at roughly half the speed.  Default 0 (FMA / ex2.approx fast path; both
+ * modes are run-to-run deterministic and within the 1e-4 tolerance on Q). */
+enum { DCRF_OPT_EXACT_ARITHMETIC = 1 };
+int dcrf_set_option(dcrf_t *h, int option, int value);
 /* block the calling thread until everything enqueued on the handle's stream has finished */
 int dcrf_synchronize(dcrf_t *h);
 

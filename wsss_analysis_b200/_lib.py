@@ -22,6 +22,7 @@ SIGNATURES = {
     "dcrf_create_nd": (_i, [_i, _i, _i, _vp, C.POINTER(_vp)]),
     "dcrf_create_batch": (_i, [_i, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "dcrf_destroy": (None, [_vp]),
+    "dcrf_set_option": (_i, [_vp, _i, _i]),
     "dcrf_synchronize": (_i, [_vp]),
     "dcrf_set_unary": (_i, [_vp, _vp, _i]),
     "dcrf_add_pairwise_gaussian": (_i, [_vp, _f, _f, _i, _vp, _i, _i]),

@@ -40,6 +40,7 @@ struct dcrf_handle {
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
     bool unary_set = false, q_valid = false;
+    bool exact = false;  // DCRF_OPT_EXACT_ARITHMETIC
     std::vector<std::unique_ptr<Pairwise>> pw;
     Profiler prof;
 };
@@ -158,8 +159,9 @@ const T *to_device(dcrf_handle *h, const T *src, size_t count, int on_device, De
 
 // splat + (d+1) blurs of pairwise k applied to `in` (pixel-major Lp); returns the blurred buffer
 const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int Lp, bool pre_norm,
-                               bool seq, float *bufA, float *bufB) {
-    launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, h->stream);
+                               bool seq, float *bufA, float *bufB, bool fast = false) {
+    if (fast) launch_splat_fast(p.lat, in, bufA, Lp, h->stream);  // pre-norm folded into the weights
+    else launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, h->stream);
     float *cur = bufA, *nxt = bufB;
     for (int j = 0; j <= p.lat.d; j++) {
         launch_blur(p.lat, j, cur, nxt, Lp, seq, h->stream);
@@ -167,6 +169,9 @@ const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int
     }
     return cur;
 }
+
+bool pre_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
+bool post_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
 
 void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const float *compat, int ktype,
                   int ntype) {
@@ -216,13 +221,12 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         p->norm.alloc(Ntot, s);
         launch_norm_finalize(sliced.p, 4, p->norm.p, Ntot, ntype, s);
     }
+    launch_pack_fast_tables(p->lat, pre_norm(ntype) ? p->norm.p : nullptr, s);
     p->valA.alloc((size_t)p->lat.M * Lp, s);
     p->valB.alloc((size_t)p->lat.M * Lp, s);
     h->pw.push_back(std::move(p));
 }
 
-bool pre_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
-bool post_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
 
 SliceTerm make_term(Pairwise &p, const float *blurred) {
     SliceTerm t;
@@ -235,6 +239,7 @@ SliceTerm make_term(Pairwise &p, const float *blurred) {
     t.alpha = 1.0f / (1.0f + powf(2.0f, (float)-p.lat.d));
     t.d = p.lat.d;
     t.compat_kind = p.compat_kind;
+    t.ent = p.lat.ent.p;
     return t;
 }
 
@@ -250,12 +255,14 @@ void start_inference(dcrf_handle *h) {
 void step_inference(dcrf_handle *h) {
     DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "stepInference before startInference");
     const bool seq = h->L <= 2;
+    const bool fast = !h->exact && !seq && h->geom.Ntot * (int64_t)(h->Lp / 4) < ((int64_t)1 << 31);
     SliceArgs a;
     memset(&a, 0, sizeof(a));
     a.seq = seq ? 1 : 0;
+    a.fast = fast ? 1 : 0;
     for (auto &p : h->pw) {
         const float *blurred =
-            filter_to_lattice(h, *p, h->Q.p, h->Lp, pre_norm(p->ntype), seq, p->valA.p, p->valB.p);
+            filter_to_lattice(h, *p, h->Q.p, h->Lp, pre_norm(p->ntype), seq, p->valA.p, p->valB.p, fast);
         a.term[a.n_terms++] = make_term(*p, blurred);
     }
     launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
@@ -330,6 +337,14 @@ void dcrf_destroy(dcrf_t *h) {
     } catch (...) {
     }
     delete h;
+}
+
+int dcrf_set_option(dcrf_t *h, int option, int value) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC, DCRF_EINVAL, "unknown option");
+        h->exact = value != 0;
+    });
 }
 
 int dcrf_synchronize(dcrf_t *h) {

@@ -142,6 +142,10 @@ struct Lattice {
     DevBuf<int32_t> csr_start;     // [M+1] rows of the transposed incidence (splat as a gather)
     DevBuf<int32_t> csr_pix;       // [E] pixel of each sorted entry (ascending entry order per row)
     DevBuf<float> csr_w;           // [E] barycentric weight of each sorted entry
+    // packed tables of the fast path (one 64-bit load per entry instead of two 32-bit loads)
+    DevBuf<int2> ent;              // [E] (vertex id, barycentric weight bits) of entry e
+    DevBuf<int2> csr_ent;          // [E] (pixel, weight * pre-norm[pixel] bits) of each sorted entry
+    DevBuf<int> row_counter;       // [1] dynamic row-chunk dispenser of the fast splat
 };
 
 void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
@@ -160,16 +164,21 @@ struct SliceTerm {
     float alpha;
     int d;
     int compat_kind;
+    const int2 *ent;      // packed (vertex id, weight) per entry (fast path)
 };
 struct SliceArgs {
     SliceTerm term[kMaxPairwise];
     int n_terms;
     int seq;  // value_size <= 2 association (A.4)
+    int fast; // fused-multiply-add / fast-exp path allowed (handle not in exact-arithmetic mode)
 };
 
 // values <- splat of (pre ? norm (.) Q : Q)       (A.4 splat, A.5 pre-scaling)
 void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, float *val, int Lp,
                   cudaStream_t s);
+// fast path: packed tables, weights pre-multiplied by the pre-normalisation, FMA accumulation
+void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s);
+void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s);
 // out <- in + 0.5 (in[n1] + in[n2]) along axis j  (A.4 blur)
 void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
                  cudaStream_t s);

@@ -12,6 +12,8 @@
 // HBM-bound byte work: no tensor cores.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dcrf {
@@ -57,54 +59,209 @@ __device__ __forceinline__ float4 scale4(const float4 q, float n) {
 
 // ---------------------------------------------------------------------------------------------
 // splat: val[v] = sum over the row's entries, ascending entry order, of w * (norm[p] * Q[p])
-// (same summation order as the sequential pixel scan of A.4 => bit-identical lattice values)
+// (same summation order as the sequential pixel scan of A.4 => bit-identical lattice values).
+//
+// Flat mapping: thread t owns float4 column c = t % g of the rows v = t / g, t/g + n_groups, ...
+// (persistent loop).  Rows differ a lot in length (1 .. thousands of entries), so the loop is
+// flattened: every trip handles one batch of <= SB entries of the thread's CURRENT row and moves on
+// to its next row when the row is finished.  Lanes of a warp therefore never wait for the longest
+// row of the warp, and every trip keeps SB independent gathers in flight.
 // ---------------------------------------------------------------------------------------------
+constexpr int kSplatBatch = 4;
+constexpr int kSplatBlocksPerSM = 6;
+
 template <int G, bool PRE>
 __global__ void __launch_bounds__(kThreads) splat_kernel(
     const int32_t *__restrict__ csr_start, const int32_t *__restrict__ csr_pix,
     const float *__restrict__ csr_w, const float *__restrict__ Q, const float *__restrict__ norm,
     float *__restrict__ val, int64_t M, int g_rt) {
-    const RowMap<G> rm(g_rt);
-    const int64_t v = rm.row();
-    if (!rm.lane_active() || v >= M) return;
-    const int g = rm.g, c = rm.col();
-    int s = csr_start[v];
-    const int s1 = csr_start[v + 1];
+    constexpr int SB = kSplatBatch;
+    const int g = G ? G : g_rt;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t n_groups = ((int64_t)gridDim.x * kThreads) / g;
+    int64_t v = tid / g;
+    const int c = (int)(tid - v * g);
+    if (v >= n_groups || v >= M) return;
+    int s = csr_start[v], s1 = csr_start[v + 1];
+    // row bounds of the NEXT row are fetched one row ahead so that a row switch costs no extra trip
+    int64_t vn = v + n_groups;
+    int ns = 0, ns1 = 0;
+    if (vn < M) { ns = csr_start[vn]; ns1 = csr_start[vn + 1]; }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (; s + 4 <= s1; s += 4) {
-        int p[4];
-        float w[4];
-        float4 q[4];
-        float n[4];
+    for (;;) {
+        int p[SB];
+        float w[SB];
+        float4 q[SB];
+        float n[SB];
+        const int cnt = min(SB, s1 - s);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            p[i] = csr_pix[s + i];
-            w[i] = csr_w[s + i];
+        for (int i = 0; i < SB; i++) {
+            const bool ok = i < cnt;
+            p[i] = ok ? csr_pix[s + i] : 0;
+            w[i] = ok ? csr_w[s + i] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            q[i] = ldg4(Q + ((int64_t)p[i] * g + c) * 4);
-            if (PRE) n[i] = norm[p[i]];
+        for (int i = 0; i < SB; i++) {
+            if (i < cnt) {
+                q[i] = ldg4(Q + ((int64_t)p[i] * g + c) * 4);
+                if (PRE) n[i] = norm[p[i]];
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (PRE) q[i] = scale4(q[i], n[i]);
-            mul_add(acc, w[i], q[i]);
+        for (int i = 0; i < SB; i++) {
+            if (i < cnt) {
+                if (PRE) q[i] = scale4(q[i], n[i]);
+                mul_add(acc, w[i], q[i]);
+            }
+        }
+        s += cnt;
+        if (s >= s1) {
+            st4(val + (v * g + c) * 4, acc);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            v = vn;
+            if (v >= M) break;
+            s = ns;
+            s1 = ns1;
+            vn = v + n_groups;
+            if (vn < M) { ns = csr_start[vn]; ns1 = csr_start[vn + 1]; }
         }
     }
-    for (; s < s1; s++) {
-        const int p = csr_pix[s];
-        const float w = csr_w[s];
-        float4 q = ldg4(Q + ((int64_t)p * g + c) * 4);
-        if (PRE) q = scale4(q, norm[p]);
-        mul_add(acc, w, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (default): same algorithm, leaner instruction stream.  The exact kernels above spend
+// most of their issue slots on separately rounded multiplies/adds, 64-bit index math, per-entry
+// norm gathers and libm-accurate exp/div; ncu showed them issue-bound (IPC 0.6/SMSP at < 30 % of HBM
+// peak).  Here: (pixel, weight) and (vertex, weight) pairs are packed into one 64-bit load, the
+// pre-normalisation is folded into the splat weight at build time, accumulation uses FMA, indices
+// are 32-bit.  Results differ from the exact path by float rounding only (~1e-7 relative on the
+// lattice values); run-to-run determinism is unchanged (fixed summation order, no atomics).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pack_fast_tables_kernel(
+    const int32_t *__restrict__ offset, const float *__restrict__ bary, const int32_t *__restrict__ csr_pix,
+    const float *__restrict__ csr_w, const float *__restrict__ norm_pre, int2 *__restrict__ ent,
+    int2 *__restrict__ csr_ent, int64_t E) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    ent[e] = make_int2(offset[e], __float_as_int(bary[e]));
+    const int p = csr_pix[e];
+    float w = csr_w[e];
+    if (norm_pre) w = __fmul_rn(w, norm_pre[p]);
+    csr_ent[e] = make_int2(p, __float_as_int(w));
+}
+
+__device__ __forceinline__ void fma4(float4 &acc, float w, const float4 q) {
+    acc.x = fmaf(w, q.x, acc.x);
+    acc.y = fmaf(w, q.y, acc.y);
+    acc.z = fmaf(w, q.z, acc.z);
+    acc.w = fmaf(w, q.w, acc.w);
+}
+
+// Work distribution: rows differ wildly in length (bilateral lattice: median 6, p99 46, max > 150
+// entries), so rows are handed out dynamically.  A warp claims chunks of 32 consecutive rows with
+// one atomicAdd, keeps the chunk's 33 row bounds in registers (one coalesced load), and its
+// 32/g lane groups pull the next unclaimed row of the chunk whenever they finish one.  Every trip
+// of the (warp-uniform) loop handles one batch of <= SB entries of each group's current row.  Each
+// row is still summed by ONE group in ascending entry order, so the result does not depend on the
+// schedule: bit-deterministic run to run.
+constexpr int kSplatChunk = 32;
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
+                                                              const int2 *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M, int g_rt,
+                                                              int *__restrict__ row_counter) {
+    constexpr int SB = kSplatBatch;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = G ? G : g_rt;
+    const int lane = threadIdx.x & 31;
+    const int gpw = 32 / g;             // lane groups per warp
+    const int sub = lane / g;           // my group
+    const int c = lane - sub * g;       // my float4 column
+    const bool lane_on = sub < gpw;
+    const unsigned leader_bit = 1u << (sub * g);
+    // warp-uniform queue state
+    int q_base = 0, q_next = 0, q_end = 0;  // rows [q_next, q_end) of the chunk starting at q_base
+    int bounds = 0, bound_last = 0;         // lane i holds csr_start[q_base + i]; bound_last = csr_start[q_base + 32]
+    bool exhausted = false;
+    // per-group state: current row v with entries [s, s1); e_cur = its current batch, already loaded
+    int v = -1, s = 0, s1 = 0, cnt_cur = 0;
+    int2 e_cur[SB];
+#pragma unroll
+    for (int i = 0; i < SB; i++) e_cur[i] = make_int2(0, 0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Software pipeline: in every trip the row gathers of batch k and the entry loads of batch k+1
+    // (possibly of the group's NEXT row, claimed one trip ahead) are in flight together.
+    for (;;) {
+        // 1. gathers of the current batch
+        float4 q[SB];
+#pragma unroll
+        for (int i = 0; i < SB; i++) {
+            q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < cnt_cur) q[i] = __ldg(Q4 + ((unsigned)e_cur[i].x * g + c));
+        }
+        // 2. choose the next batch: same row, or claim a new row from the warp's chunk
+        const bool row_ends = v < 0 || s + SB >= s1;
+        int nv = v, ns = s + SB, ns1 = s1;
+        const bool need = lane_on && row_ends;
+        const unsigned need_mask = __ballot_sync(FULL, need && c == 0);
+        if (need_mask) {
+            if (q_next >= q_end && !exhausted) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(row_counter, kSplatChunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= M) {
+                    exhausted = true;
+                } else {
+                    q_base = q_next = base;
+                    q_end = min(base + kSplatChunk, M);
+                    bounds = csr_start[min(base + lane, M)];
+                    bound_last = csr_start[q_end];
+                }
+            }
+            const int rank = __popc(need_mask & (leader_bit - 1));
+            const int row = q_next + rank;
+            const bool take = need && row < q_end;
+            const int rel = take ? row - q_base : 0;
+            const int b0 = __shfl_sync(FULL, bounds, rel & 31);
+            int b1 = __shfl_sync(FULL, bounds, (rel + 1) & 31);
+            if (rel + 1 == q_end - q_base) b1 = bound_last;
+            if (need) {
+                nv = take ? row : -1;
+                ns = b0;
+                ns1 = b1;
+            }
+            q_next = min(q_end, q_next + __popc(need_mask));
+        }
+        // 3. entry loads of the next batch
+        const int ncnt = nv >= 0 ? min(SB, ns1 - ns) : 0;
+        int2 e_next[SB];
+#pragma unroll
+        for (int i = 0; i < SB; i++) e_next[i] = (i < ncnt) ? __ldg(csr_ent + ns + i) : make_int2(0, 0);
+        // 4. consume the current batch (padded slots add 0 * 0)
+#pragma unroll
+        for (int i = 0; i < SB; i++) fma4(acc, __int_as_float(e_cur[i].y), q[i]);
+        if (v >= 0 && row_ends) {
+            val4[(unsigned)v * g + c] = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // 5. rotate
+        v = nv;
+        s = ns;
+        s1 = ns1;
+        cnt_cur = ncnt;
+#pragma unroll
+        for (int i = 0; i < SB; i++) e_cur[i] = e_next[i];
+        if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
     }
-    st4(val + (v * g + c) * 4, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // blur along one axis: out[v] = in[v] + 0.5 * (in[n1] + in[n2]); absent neighbour = zero row.
 // SEQ reproduces the value_size<=2 association (sum in float, 0.5* and outer add in double).
+// Flat mapping over the M*g float4 elements, BU elements per thread: all neighbour ids and own
+// rows are requested first, then the 2*BU dependent gathers, so 3*BU 128-bit loads are in flight.
 // ---------------------------------------------------------------------------------------------
 template <bool SEQ>
 __device__ __forceinline__ float blur1(float o, float a, float b) {
@@ -112,25 +269,47 @@ __device__ __forceinline__ float blur1(float o, float a, float b) {
     return __fadd_rn(o, __fmul_rn(0.5f, __fadd_rn(a, b)));
 }
 
+constexpr int kBlurUnroll = 4;
+
 template <int G, bool SEQ>
 __global__ void __launch_bounds__(kThreads) blur_kernel(const int2 *__restrict__ neigh,
                                                         const float *__restrict__ in,
                                                         float *__restrict__ out, int64_t M, int g_rt) {
-    const RowMap<G> rm(g_rt);
-    const int64_t v = rm.row();
-    if (!rm.lane_active() || v >= M) return;
-    const int g = rm.g, c = rm.col();
-    const int2 nb = neigh[v];
-    const float4 o = ldg4(in + (v * g + c) * 4);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (nb.x >= 0) a = ldg4(in + ((int64_t)nb.x * g + c) * 4);
-    if (nb.y >= 0) b = ldg4(in + ((int64_t)nb.y * g + c) * 4);
-    float4 r;
-    r.x = blur1<SEQ>(o.x, a.x, b.x);
-    r.y = blur1<SEQ>(o.y, a.y, b.y);
-    r.z = blur1<SEQ>(o.z, a.z, b.z);
-    r.w = blur1<SEQ>(o.w, a.w, b.w);
-    st4(out + (v * g + c) * 4, r);
+    constexpr int BU = kBlurUnroll;
+    const int g = G ? G : g_rt;
+    const int64_t total = M * g;
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * BU) + threadIdx.x;
+    int64_t idx[BU];
+    int c[BU];
+    int2 nb[BU];
+    float4 o[BU], a[BU], b[BU];
+#pragma unroll
+    for (int u = 0; u < BU; u++) {
+        idx[u] = base + (int64_t)u * kThreads;
+        const bool ok = idx[u] < total;
+        const int64_t v = ok ? idx[u] / g : 0;
+        c[u] = (int)(idx[u] - v * g);
+        nb[u] = ok ? neigh[v] : make_int2(-1, -1);
+        o[u] = ok ? ldg4(in + idx[u] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < BU; u++) {
+        a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[u] = a[u];
+        if (nb[u].x >= 0) a[u] = ldg4(in + ((int64_t)nb[u].x * g + c[u]) * 4);
+        if (nb[u].y >= 0) b[u] = ldg4(in + ((int64_t)nb[u].y * g + c[u]) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < BU; u++) {
+        if (idx[u] < total) {
+            float4 r;
+            r.x = blur1<SEQ>(o[u].x, a[u].x, b[u].x);
+            r.y = blur1<SEQ>(o[u].y, a[u].y, b[u].y);
+            r.z = blur1<SEQ>(o[u].z, a[u].z, b[u].z);
+            r.w = blur1<SEQ>(o[u].w, a[u].w, b[u].w);
+            st4(out + idx[u] * 4, r);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,6 +338,33 @@ __device__ __forceinline__ float4 slice_row(const int32_t *__restrict__ offset,
     }
     return acc;
 }
+
+// compile-time-D slice split in two phases so that callers can put the loads of SEVERAL terms in
+// flight before consuming any of them: gather() issues the D+1 index/weight loads and then the D+1
+// row gathers, reduce() accumulates in r order with the non-SEQ association (w*alpha)*v.
+template <int D>
+struct SliceGather {
+    float4 v[D + 1];
+    float w[D + 1];
+    __device__ __forceinline__ void gather(const int32_t *__restrict__ offset, const float *__restrict__ bary,
+                                           const float *__restrict__ val, int64_t p, int g, int c) {
+        int o[D + 1];
+        const int64_t base = p * (D + 1);
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            o[r] = offset[base + r];
+            w[r] = bary[base + r];
+        }
+#pragma unroll
+        for (int r = 0; r <= D; r++) v[r] = ldg4(val + ((int64_t)o[r] * g + c) * 4);
+    }
+    __device__ __forceinline__ float4 reduce(float alpha) const {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r <= D; r++) mul_add(acc, __fmul_rn(w[r], alpha), v[r]);
+        return acc;
+    }
+};
 
 // compat( norm (.) sliced ): Potts -> (-w) * x ; diagonal -> c[l] * x[l] ; matrix -> C x
 // (matrix rows are padded to Lp with zeros; all lanes of the warp must call this)
@@ -200,7 +406,10 @@ __device__ __forceinline__ float4 apply_compat(const SliceTerm &t, float4 x, int
 // fused: slice every pairwise term, normalise, compat, unary add, softmax over labels  (A.7)
 //   t = -U ; for k: t -= compat_k( norm_k * slice_k ) ; Q = softmax_L(t)
 // ---------------------------------------------------------------------------------------------
-template <int G>
+// FAST25: exactly the reference configuration -- term 0 has d = 2, term 1 has d = 5 (Gaussian +
+// bilateral), not the value_size <= 2 association: the 9 index loads, then the 9 row gathers of both
+// terms, the unary row and both norms are all in flight before the first use.
+template <int G, bool FAST25>
 __global__ void __launch_bounds__(kThreads) slice_softmax_kernel(const SliceArgs a,
                                                                  const float *__restrict__ unary,
                                                                  float *__restrict__ Q, int64_t Ntot,
@@ -210,10 +419,32 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_kernel(const SliceArgs
     const int64_t p = rm.row();
     const bool act = rm.lane_active() && p < Ntot;
     const int64_t pc = act ? p : 0;  // inactive lanes shadow pixel 0 so that shuffles stay uniform
-    const float4 u = ldg4(unary + (pc * g + c) * 4);
-    float4 t = make_float4(-u.x, -u.y, -u.z, -u.w);
     const int Lp = g * 4;
-    for (int k = 0; k < a.n_terms; k++) {
+    float4 t;
+    if (FAST25) {
+        const SliceTerm &t0 = a.term[0];
+        const SliceTerm &t1 = a.term[1];
+        SliceGather<2> g0;
+        SliceGather<5> g1;
+        g0.gather(t0.offset, t0.bary, t0.val, pc, g, c);
+        g1.gather(t1.offset, t1.bary, t1.val, pc, g, c);
+        const float4 u = ldg4(unary + (pc * g + c) * 4);
+        const float n0 = t0.norm ? t0.norm[pc] : 1.f;
+        const float n1 = t1.norm ? t1.norm[pc] : 1.f;
+        t = make_float4(-u.x, -u.y, -u.z, -u.w);
+        float4 x = g0.reduce(t0.alpha);
+        if (t0.norm) x = scale4(x, n0);
+        float4 y = apply_compat(t0, x, g, c, Lp);
+        t.x = __fsub_rn(t.x, y.x); t.y = __fsub_rn(t.y, y.y); t.z = __fsub_rn(t.z, y.z); t.w = __fsub_rn(t.w, y.w);
+        x = g1.reduce(t1.alpha);
+        if (t1.norm) x = scale4(x, n1);
+        y = apply_compat(t1, x, g, c, Lp);
+        t.x = __fsub_rn(t.x, y.x); t.y = __fsub_rn(t.y, y.y); t.z = __fsub_rn(t.z, y.z); t.w = __fsub_rn(t.w, y.w);
+    } else {
+        const float4 u = ldg4(unary + (pc * g + c) * 4);
+        t = make_float4(-u.x, -u.y, -u.z, -u.w);
+    }
+    for (int k = 0; k < (FAST25 ? 0 : a.n_terms); k++) {
         const SliceTerm &tm = a.term[k];
         float4 x = a.seq ? slice_row<true>(tm.offset, tm.bary, tm.val, pc, tm.d, tm.alpha, g, c)
                          : slice_row<false>(tm.offset, tm.bary, tm.val, pc, tm.d, tm.alpha, g, c);
@@ -251,6 +482,83 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_kernel(const SliceArgs
         q.z = __fdiv_rn(e.z, sum);
         q.w = __fdiv_rn(e.w, sum);
         st4(Q + (p * g + c) * 4, q);
+    }
+}
+
+// Fast fused slice for the reference configuration: term 0 with d = DA, term 1 with d = DB, both
+// Potts.  t = -U + sum_k (w_k alpha_k n_k[p]) * sum_r bary_r v_r ; Q = softmax(t) with ex2.approx.
+template <int D>
+__device__ __forceinline__ float4 slice_fast_row(const int2 *__restrict__ ent, const float4 *__restrict__ val4,
+                                                 unsigned p, unsigned g, unsigned c) {
+    int2 e[D + 1];
+    float4 v[D + 1];
+    const int2 *ep = ent + (size_t)p * (D + 1);
+    if (((D + 1) & 1) == 0) {  // even entry count: 128-bit loads of two entries
+        const int4 *ep4 = reinterpret_cast<const int4 *>(ep);
+#pragma unroll
+        for (int r = 0; r < (D + 1) / 2; r++) {
+            const int4 t = __ldg(ep4 + r);
+            e[2 * r] = make_int2(t.x, t.y);
+            e[2 * r + 1] = make_int2(t.z, t.w);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r <= D; r++) e[r] = __ldg(ep + r);
+    }
+#pragma unroll
+    for (int r = 0; r <= D; r++) v[r] = __ldg(val4 + ((unsigned)e[r].x * g + c));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r <= D; r++) fma4(acc, __int_as_float(e[r].y), v[r]);
+    return acc;
+}
+
+template <int G, int DA, int DB>
+__global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const SliceArgs a,
+                                                                      const float4 *__restrict__ unary4,
+                                                                      float4 *__restrict__ Q4, unsigned Ntot,
+                                                                      int L, int g_rt) {
+    const RowMap<G> rm(g_rt);
+    const unsigned g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
+    const unsigned p = act ? (unsigned)p64 : 0u;
+    const SliceTerm &t0 = a.term[0];
+    const SliceTerm &t1 = a.term[1];
+    const float4 x0 = slice_fast_row<DA>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, g, c);
+    const float4 x1 = slice_fast_row<DB>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, g, c);
+    const float4 u = __ldg(unary4 + (p * g + c));
+    float w0 = t0.potts_w * t0.alpha, w1 = t1.potts_w * t1.alpha;
+    if (t0.norm) w0 *= __ldg(t0.norm + p);
+    if (t1.norm) w1 *= __ldg(t1.norm + p);
+    float4 t;
+    t.x = fmaf(w1, x1.x, fmaf(w0, x0.x, -u.x));
+    t.y = fmaf(w1, x1.y, fmaf(w0, x0.y, -u.y));
+    t.z = fmaf(w1, x1.z, fmaf(w0, x0.z, -u.z));
+    t.w = fmaf(w1, x1.w, fmaf(w0, x0.w, -u.w));
+    const int l0 = c * 4;
+    const float NEG = -INFINITY;
+    if (l0 + 0 >= L) t.x = NEG;
+    if (l0 + 1 >= L) t.y = NEG;
+    if (l0 + 2 >= L) t.z = NEG;
+    if (l0 + 3 >= L) t.w = NEG;
+    const float m = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane - c;
+    float mx = NEG;
+    for (int i = 0; i < (int)g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
+    constexpr float kLog2e = 1.4426950408889634f;
+    float4 e;
+    e.x = exp2f((t.x - mx) * kLog2e);  // exp2f(-inf) = 0 for the padding lanes
+    e.y = exp2f((t.y - mx) * kLog2e);
+    e.z = exp2f((t.z - mx) * kLog2e);
+    e.w = exp2f((t.w - mx) * kLog2e);
+    const float ls = (e.x + e.y) + (e.z + e.w);
+    float sum = 0.f;
+    for (int i = 0; i < (int)g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
+    if (act) {
+        const float inv = 1.0f / sum;
+        Q4[p * g + c] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
     }
 }
 
@@ -434,7 +742,8 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
                   cudaStream_t s) {
     if (lat.M == 0) return;
     const int g = Lp / 4;
-    const int nb = ceil_div(lat.M, rows_per_block(g));
+    // persistent grid: a few CTAs per SM, each thread group walks rows v, v + n_groups, ...
+    const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * kSplatBlocksPerSM);
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     DCRF_DISPATCH_G(g, {
         if (norm_pre)
@@ -447,11 +756,45 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
     DCRF_LAUNCHED();
 }
 
+void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s) {
+    if (lat.E == 0) return;
+    lat.ent.alloc(lat.E, s);
+    lat.csr_ent.alloc(lat.E, s);
+    lat.row_counter.alloc(1, s);
+    pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
+        lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, lat.ent.p, lat.csr_ent.p, lat.E);
+    DCRF_LAUNCHED();
+}
+
+template <typename K>
+static int resident_blocks_per_sm(K kernel) {
+    int n = 0;
+    DCRF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0));
+    return n > 0 ? n : 1;
+}
+
+void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
+    if (lat.M == 0) return;
+    const int g = Lp / 4;
+    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, sizeof(int), s));
+    ProfScope prof(DCRF_K_SPLAT, lat.d, s);
+    DCRF_DISPATCH_G(g, {
+        // persistent grid of exactly one resident wave; rows are claimed dynamically
+        static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G>);
+        const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
+        splat_fast_kernel<G><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_ent.p,
+                                                    reinterpret_cast<const float4 *>(Q),
+                                                    reinterpret_cast<float4 *>(val), (int)lat.M, g,
+                                                    lat.row_counter.p);
+    });
+    DCRF_LAUNCHED();
+}
+
 void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
                  cudaStream_t s) {
     if (lat.M == 0) return;
     const int g = Lp / 4;
-    const int nb = ceil_div(lat.M, rows_per_block(g));
+    const int nb = ceil_div(lat.M * g, kThreads * kBlurUnroll);
     const int2 *nbr = lat.neigh.p + (int64_t)axis * lat.M;
     ProfScope prof(DCRF_K_BLUR, lat.d, s);
     DCRF_DISPATCH_G(g, {
@@ -467,7 +810,21 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
     const int g = Lp / 4;
     const int nb = ceil_div(Ntot, rows_per_block(g));
     ProfScope prof(DCRF_K_SLICE, a.n_terms, s);
-    DCRF_DISPATCH_G(g, { slice_softmax_kernel<G><<<nb, kThreads, 0, s>>>(a, unary, Q, Ntot, L, g); });
+    const bool fast25 = a.n_terms == 2 && a.term[0].d == 2 && a.term[1].d == 5 && !a.seq;
+    const bool potts2 = fast25 && a.term[0].compat_kind == DCRF_COMPAT_POTTS &&
+                        a.term[1].compat_kind == DCRF_COMPAT_POTTS && a.term[0].ent && a.term[1].ent;
+    if (a.fast && potts2 && Ntot * g < ((int64_t)1 << 31)) {
+        DCRF_DISPATCH_G(g, {
+            slice_softmax_fast_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(
+                a, reinterpret_cast<const float4 *>(unary), reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
+        });
+        DCRF_LAUNCHED();
+        return;
+    }
+    DCRF_DISPATCH_G(g, {
+        if (fast25) slice_softmax_kernel<G, true><<<nb, kThreads, 0, s>>>(a, unary, Q, Ntot, L, g);
+        else slice_softmax_kernel<G, false><<<nb, kThreads, 0, s>>>(a, unary, Q, Ntot, L, g);
+    });
     DCRF_LAUNCHED();
 }
 

@@ -111,6 +111,10 @@ class _Model(object):
 
             torch.cuda.current_stream().synchronize()
 
+    def set_exact_arithmetic(self, on=True):
+        """Use the specification's float association literally in the iteration kernels (slower)."""
+        _lib.check(self._lib.dcrf_set_option(self._h, 1, 1 if on else 0))
+
     def synchronize(self):
         _lib.check(self._lib.dcrf_synchronize(self._h))
 
