@@ -1,0 +1,25 @@
+"""Diagnostic: per-kernel-class device time of the iteration loop at batch B (CUDA events)."""
+import sys, os
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np, torch
+import bench
+from wsss_analysis_b200 import densecrf as G
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+dev = torch.device("cuda", 0)
+imgs, unaries = bench.make_inputs(B)
+sizes = [(bench.W_IMG, bench.H_IMG)] * B
+U = torch.from_numpy(np.concatenate([u.ravel() for u in unaries])).to(dev)
+I = torch.from_numpy(np.concatenate([im.ravel() for im in imgs])).to(dev)
+Q = torch.empty(B * bench.L_LAB * bench.W_IMG * bench.H_IMG, dtype=torch.float32, device=dev)
+torch.cuda.synchronize()
+crf = G.DenseCRFBatch(sizes, bench.L_LAB, device=0)
+crf.setUnaryEnergy(U); crf.addPairwiseGaussian(sxy=3, compat=3); crf.addPairwiseBilateral(sxy=80, srgb=13, rgbim=I, compat=10)
+crf.inference_device(2, out=Q)
+crf.profile_enable(True)
+crf.inference_device(10, out=Q)
+tot = 0
+for cls, cid in (("splat", 0), ("blur", 1), ("slice", 2)):
+    for tag in ((2, 5) if cls != "slice" else (2,)):
+        ms, n = crf.profile_read(cid, tag)
+        if n: print("%s tag=%d: %d launches avg %.1f us total %.2f ms" % (cls, tag, n, ms / n * 1e3, ms)); tot += ms
+print("SB=%s B=%d iteration kernels total %.2f ms per 10 iters" % (os.environ.get("DCRF_SPLAT_SB", "4"), B, tot))

@@ -248,6 +248,8 @@ void start_inference(dcrf_handle *h) {
     SliceArgs a;
     memset(&a, 0, sizeof(a));
     a.n_terms = 0;
+    a.seq = h->L <= 2 ? 1 : 0;
+    a.fast = (!h->exact && h->L > 2) ? 1 : 0;
     launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
     h->q_valid = true;
 }

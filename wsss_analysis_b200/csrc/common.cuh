@@ -209,9 +209,12 @@ void launch_slice_pairwise_only(const SliceTerm &t, float *out, int64_t Ntot, in
 // ---------------------------------------------------------------------------------------------
 // out[i] = exclusive prefix sum of in[0..i), out[n] = total.  in/out may alias.  int32.
 void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
-// stable LSD radix sort of (key, value) pairs on the low `bits` bits of key.  Results end in
-// keys_a / vals_a; *_b are scratch of the same size.
-void radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+// stable LSD radix sort of (key, value) pairs on the low `bits` bits of key (8 bits per pass).
+// Returns 0 when the sorted pairs ended in keys_a / vals_a, 1 when they ended in keys_b / vals_b.
+int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                               const std::vector<int64_t> &seg_start, const int32_t *d_key_base,
+                               int local_bits, cudaStream_t s);
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
                       int64_t n, int bits, cudaStream_t s);
 
 }  // namespace dcrf

@@ -165,6 +165,7 @@ __device__ __forceinline__ void fma4(float4 &acc, float w, const float4 q) {
 // row is still summed by ONE group in ascending entry order, so the result does not depend on the
 // schedule: bit-deterministic run to run.
 constexpr int kSplatChunk = 32;
+constexpr int kSplatSuper = 8;  // chunks per super-chunk (256 consecutive rows per CTA at a time)
 
 template <int G>
 __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
@@ -181,6 +182,9 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
     const int c = lane - sub * g;       // my float4 column
     const bool lane_on = sub < gpw;
     const unsigned leader_bit = 1u << (sub * g);
+    __shared__ unsigned cta_chunks;
+    if (threadIdx.x == 0) cta_chunks = 0;
+    __syncthreads();
     // warp-uniform queue state
     int q_base = 0, q_next = 0, q_end = 0;  // rows [q_next, q_end) of the chunk starting at q_base
     int bounds = 0, bound_last = 0;         // lane i holds csr_start[q_base + i]; bound_last = csr_start[q_base + 32]
@@ -208,8 +212,17 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
         const unsigned need_mask = __ballot_sync(FULL, need && c == 0);
         if (need_mask) {
             if (q_next >= q_end && !exhausted) {
+                // Chunks are dealt per CTA: the CTA owns the super-chunks blockIdx.x, blockIdx.x +
+                // gridDim.x, ... (kSplatSuper consecutive 32-row chunks each) and its warps pull the
+                // next chunk from a shared-memory counter.  The warps of an SM therefore gather from
+                // the same neighbourhood of Q (L1 reuse), and no global atomic is needed.
                 int base = 0;
-                if (lane == 0) base = atomicAdd(row_counter, kSplatChunk);
+                if (lane == 0) {
+                    const unsigned n = atomicAdd(&cta_chunks, 1u);
+                    const unsigned long long sc = blockIdx.x + (unsigned long long)(n / kSplatSuper) * gridDim.x;
+                    const unsigned long long b = (sc * kSplatSuper + n % kSplatSuper) * kSplatChunk;
+                    base = b < (unsigned long long)M ? (int)b : M;
+                }
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= M) {
                     exhausted = true;
@@ -562,6 +575,44 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const Slic
     }
 }
 
+// Q0 = softmax(-U) (startInference), fast-math variant of slice_softmax_kernel with no terms
+template <int G>
+__global__ void __launch_bounds__(kThreads) softmax_unary_fast_kernel(const float4 *__restrict__ unary4,
+                                                                      float4 *__restrict__ Q4, unsigned Ntot,
+                                                                      int L, int g_rt) {
+    const RowMap<G> rm(g_rt);
+    const unsigned g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
+    const unsigned p = act ? (unsigned)p64 : 0u;
+    const float4 u = __ldg(unary4 + (p * g + c));
+    float4 t = make_float4(-u.x, -u.y, -u.z, -u.w);
+    const int l0 = c * 4;
+    const float NEG = -INFINITY;
+    if (l0 + 0 >= L) t.x = NEG;
+    if (l0 + 1 >= L) t.y = NEG;
+    if (l0 + 2 >= L) t.z = NEG;
+    if (l0 + 3 >= L) t.w = NEG;
+    const float m = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane - c;
+    float mx = NEG;
+    for (int i = 0; i < (int)g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
+    constexpr float kLog2e = 1.4426950408889634f;
+    float4 e;
+    e.x = exp2f((t.x - mx) * kLog2e);
+    e.y = exp2f((t.y - mx) * kLog2e);
+    e.z = exp2f((t.z - mx) * kLog2e);
+    e.w = exp2f((t.w - mx) * kLog2e);
+    const float ls = (e.x + e.y) + (e.z + e.w);
+    float sum = 0.f;
+    for (int i = 0; i < (int)g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
+    if (act) {
+        const float inv = 1.0f / sum;
+        Q4[p * g + c] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
+    }
+}
+
 // slice of one lattice without any epilogue (norm construction, test hook)
 template <int G, bool SEQ>
 __global__ void __launch_bounds__(kThreads) slice_plain_kernel(
@@ -614,49 +665,70 @@ __global__ void __launch_bounds__(kThreads) fill_ones_col0_kernel(float *__restr
 // ---------------------------------------------------------------------------------------------
 // layout changes at the API boundary: (L, N_b) row-major blocks <-> (Ntot, Lp) pixel-major
 // ---------------------------------------------------------------------------------------------
-constexpr int kTP = 32;  // pixels per tile
-// grid (ceil(maxN/32), B), block (32, 8)
-__global__ void ln_to_pm_kernel(const float *__restrict__ ln, float *__restrict__ pm,
-                                const int *__restrict__ pix_start, int L, int Lp) {
-    extern __shared__ float tile[];  // [Lp][33]
+constexpr int kTP = 128;  // pixels per tile; 256 threads per CTA; tile[Lp][kTP + 1] floats of shared memory
+// grid (ceil(maxN / 128), B).  Label rows are read 128 pixels at a time (4 independent coalesced
+// loads per lane), the pixel-major side moves as float4.
+__global__ void __launch_bounds__(kThreads) ln_to_pm_kernel(const float *__restrict__ ln,
+                                                            float *__restrict__ pm,
+                                                            const int *__restrict__ pix_start, int L, int Lp) {
+    extern __shared__ float tile[];
     const int b = blockIdx.y;
     const int64_t ps = pix_start[b];
     const int Nb = (int)(pix_start[b + 1] - ps);
     const int p0 = blockIdx.x * kTP;
     if (p0 >= Nb) return;
-    const float *src = ln + ps * L;  // image block (L, Nb)
-    for (int l = threadIdx.y; l < Lp; l += blockDim.y) {
-        const int p = p0 + threadIdx.x;
-        tile[l * (kTP + 1) + threadIdx.x] = (l < L && p < Nb) ? src[(int64_t)l * Nb + p] : 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *src = ln + ps * L + p0;  // image block (L, Nb)
+    const int np = min(kTP, Nb - p0);
+    for (int l = warp; l < Lp; l += kWarps) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pp = lane + 32 * k;
+            v[k] = (l < L && pp < np) ? src[(int64_t)l * Nb + pp] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) tile[l * (kTP + 1) + lane + 32 * k] = v[k];
     }
     __syncthreads();
-    const int np = min(kTP, Nb - p0);
-    float *dst = pm + (ps + p0) * Lp;
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < np * Lp; i += blockDim.x * blockDim.y) {
-        const int pp = i / Lp, l = i - pp * Lp;
-        dst[i] = tile[l * (kTP + 1) + pp];
+    float4 *dst = reinterpret_cast<float4 *>(pm + (ps + p0) * Lp);
+    const int g = Lp >> 2;
+    for (int i = threadIdx.x; i < np * g; i += kThreads) {
+        const int pp = i / g, l = (i - pp * g) * 4;
+        dst[i] = make_float4(tile[l * (kTP + 1) + pp], tile[(l + 1) * (kTP + 1) + pp],
+                             tile[(l + 2) * (kTP + 1) + pp], tile[(l + 3) * (kTP + 1) + pp]);
     }
 }
 
-__global__ void pm_to_ln_kernel(const float *__restrict__ pm, float *__restrict__ ln,
-                                const int *__restrict__ pix_start, int L, int Lp) {
-    extern __shared__ float tile[];  // [Lp][33]
+__global__ void __launch_bounds__(kThreads) pm_to_ln_kernel(const float *__restrict__ pm,
+                                                            float *__restrict__ ln,
+                                                            const int *__restrict__ pix_start, int L, int Lp) {
+    extern __shared__ float tile[];
     const int b = blockIdx.y;
     const int64_t ps = pix_start[b];
     const int Nb = (int)(pix_start[b + 1] - ps);
     const int p0 = blockIdx.x * kTP;
     if (p0 >= Nb) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int np = min(kTP, Nb - p0);
-    const float *src = pm + (ps + p0) * Lp;
-    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < np * Lp; i += blockDim.x * blockDim.y) {
-        const int pp = i / Lp, l = i - pp * Lp;
-        tile[l * (kTP + 1) + pp] = src[i];
+    const float4 *src = reinterpret_cast<const float4 *>(pm + (ps + p0) * Lp);
+    const int g = Lp >> 2;
+    for (int i = threadIdx.x; i < np * g; i += kThreads) {
+        const int pp = i / g, l = (i - pp * g) * 4;
+        const float4 v = __ldg(src + i);
+        tile[l * (kTP + 1) + pp] = v.x;
+        tile[(l + 1) * (kTP + 1) + pp] = v.y;
+        tile[(l + 2) * (kTP + 1) + pp] = v.z;
+        tile[(l + 3) * (kTP + 1) + pp] = v.w;
     }
     __syncthreads();
-    float *dst = ln + ps * L;
-    for (int l = threadIdx.y; l < L; l += blockDim.y) {
-        const int p = p0 + threadIdx.x;
-        if (p < Nb) dst[(int64_t)l * Nb + p] = tile[l * (kTP + 1) + threadIdx.x];
+    float *dst = ln + ps * L + p0;
+    for (int l = warp; l < L; l += kWarps) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pp = lane + 32 * k;
+            if (pp < np) dst[(int64_t)l * Nb + pp] = tile[l * (kTP + 1) + pp];
+        }
     }
 }
 
@@ -776,7 +848,6 @@ static int resident_blocks_per_sm(K kernel) {
 void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
     if (lat.M == 0) return;
     const int g = Lp / 4;
-    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, sizeof(int), s));
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     DCRF_DISPATCH_G(g, {
         // persistent grid of exactly one resident wave; rows are claimed dynamically
@@ -813,6 +884,14 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
     const bool fast25 = a.n_terms == 2 && a.term[0].d == 2 && a.term[1].d == 5 && !a.seq;
     const bool potts2 = fast25 && a.term[0].compat_kind == DCRF_COMPAT_POTTS &&
                         a.term[1].compat_kind == DCRF_COMPAT_POTTS && a.term[0].ent && a.term[1].ent;
+    if (a.fast && a.n_terms == 0 && !a.seq && Ntot * g < ((int64_t)1 << 31)) {
+        DCRF_DISPATCH_G(g, {
+            softmax_unary_fast_kernel<G><<<nb, kThreads, 0, s>>>(reinterpret_cast<const float4 *>(unary),
+                                                               reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
+        });
+        DCRF_LAUNCHED();
+        return;
+    }
     if (a.fast && potts2 && Ntot * g < ((int64_t)1 << 31)) {
         DCRF_DISPATCH_G(g, {
             slice_softmax_fast_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(
@@ -876,15 +955,21 @@ static int max_image_pixels(const BatchGeom &g) {
 
 void launch_ln_to_pm(const float *ln, float *pm, const BatchGeom &g, int L, int Lp, cudaStream_t s) {
     if (g.Ntot == 0) return;
-    dim3 grid(ceil_div(max_image_pixels(g), kTP), g.B), block(kTP, 8);
-    ln_to_pm_kernel<<<grid, block, sizeof(float) * Lp * (kTP + 1), s>>>(ln, pm, g.d_pix_start, L, Lp);
+    dim3 grid(ceil_div(max_image_pixels(g), kTP), g.B);
+    const size_t smem = sizeof(float) * Lp * (kTP + 1);
+    if (smem > 48 * 1024)
+        DCRF_CUDA(cudaFuncSetAttribute(ln_to_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_to_pm_kernel<<<grid, kThreads, smem, s>>>(ln, pm, g.d_pix_start, L, Lp);
     DCRF_LAUNCHED();
 }
 
 void launch_pm_to_ln(const float *pm, float *ln, const BatchGeom &g, int L, int Lp, cudaStream_t s) {
     if (g.Ntot == 0) return;
-    dim3 grid(ceil_div(max_image_pixels(g), kTP), g.B), block(kTP, 8);
-    pm_to_ln_kernel<<<grid, block, sizeof(float) * Lp * (kTP + 1), s>>>(pm, ln, g.d_pix_start, L, Lp);
+    dim3 grid(ceil_div(max_image_pixels(g), kTP), g.B);
+    const size_t smem = sizeof(float) * Lp * (kTP + 1);
+    if (smem > 48 * 1024)
+        DCRF_CUDA(cudaFuncSetAttribute(pm_to_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pm_to_ln_kernel<<<grid, kThreads, smem, s>>>(pm, ln, g.d_pix_start, L, Lp);
     DCRF_LAUNCHED();
 }
 

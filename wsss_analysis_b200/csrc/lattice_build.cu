@@ -19,6 +19,8 @@
 // exactly "id = rank of the key's first occurrence in pixel-major, remainder-minor scan order".
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dcrf {
@@ -468,13 +470,19 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     ka.alloc(E, s); va.alloc(E, s); kb.alloc(E, s); vb.alloc(E, s);
     iota_copy_kernel<<<nbe, kThreads, 0, s>>>(out.offset.p, ka.p, va.p, E);
     DCRF_LAUNCHED();
+    // per-image segments: keys local to an image need fewer radix passes than batch-global ids
+    int64_t max_mb = 1;
+    std::vector<int64_t> ent_start(B + 1);
+    for (int b = 0; b <= B; b++) ent_start[b] = g.pix_start[b] * d1;
+    for (int b = 0; b < B; b++) max_mb = std::max<int64_t>(max_mb, out.vert_start[b + 1] - out.vert_start[b]);
     int bits = 1;
-    while (((int64_t)1 << bits) < M) bits++;
-    radix_sort_pairs(ka.p, va.p, kb.p, vb.p, E, bits, s);
+    while (((int64_t)1 << bits) < max_mb) bits++;
+    const int in_b = segmented_radix_sort_pairs(ka.p, va.p, kb.p, vb.p, ent_start, d_vert_start.p, bits, s);
+    const uint32_t *sk = in_b ? kb.p : ka.p, *sv = in_b ? vb.p : va.p;
     out.csr_start.alloc(M + 1, s);
     out.csr_pix.alloc(E, s);
     out.csr_w.alloc(E, s);
-    csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(ka.p, va.p, out.bary.p, d1, E, M, out.csr_start.p,
+    csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(sk, sv, out.bary.p, d1, E, M, out.csr_start.p,
                                                 out.csr_pix.p, out.csr_w.p);
     DCRF_LAUNCHED();
 }

@@ -1,6 +1,8 @@
 // primitives.cu -- hand-written device-wide exclusive scan and stable LSD radix sort (sm_100a).
 // Used only by lattice construction (vertex numbering and the splat's transposed incidence rows).
 // Everything here is integer work: results are bit-deterministic.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dcrf {
@@ -200,18 +202,164 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
     }
 }
 
+
+// ---------------- segmented radix sort ----------------
+// Sorts (key, value) pairs inside S consecutive segments (the images of a batch) by
+// (key - key_base[segment]), stable, LSD.  Keys of a segment are vertex ids local to one image, so
+// they need ~17-20 bits instead of the ~22-24 bits of batch-global ids: two passes of <= 10 bits
+// instead of three or four of 8.  Every tile of kSortTile pairs belongs to exactly one segment; the
+// histogram is laid out [segment][digit][tile of the segment], so that ONE exclusive scan over it
+// yields the global output position of every (segment, digit, tile) bucket.
+constexpr int kSegMaxDigitBits = 10;
+constexpr int kSegMaxRadix = 1 << kSegMaxDigitBits;
+
+struct SegInfo {
+    const int32_t *seg_start;   // [S+1] first pair of each segment
+    const int32_t *key_base;    // [S]   subtracted from the keys of the segment
+    const int32_t *tile_base;   // [S+1] first tile of each segment
+    int S;
+};
+
+__device__ __forceinline__ int seg_of_tile(const SegInfo &si, int tile) {
+    int lo = 0, hi = si.S - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (si.tile_base[mid] <= tile) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint32_t *__restrict__ keys,
+                                                                      int32_t *__restrict__ hist, SegInfo si,
+                                                                      int shift, int digit_bits) {
+    __shared__ int h[kSegMaxRadix];
+    const int radix = 1 << digit_bits;
+    for (int i = threadIdx.x; i < radix; i += kSortThreads) h[i] = 0;
+    __syncthreads();
+    const int seg = seg_of_tile(si, blockIdx.x);
+    const int t = blockIdx.x - si.tile_base[seg];
+    const int tiles = si.tile_base[seg + 1] - si.tile_base[seg];
+    const int64_t base = (int64_t)si.seg_start[seg] + (int64_t)t * kSortTile;
+    const int64_t end = si.seg_start[seg + 1];
+    const uint32_t kb = (uint32_t)si.key_base[seg];
+#pragma unroll
+    for (int i = 0; i < kSortRounds; i++) {
+        const int64_t idx = base + (int64_t)i * kSortThreads + threadIdx.x;
+        if (idx < end) atomicAdd(&h[((keys[idx] - kb) >> shift) & (radix - 1)], 1);
+    }
+    __syncthreads();
+    int32_t *hs = hist + (int64_t)radix * si.tile_base[seg];
+    for (int i = threadIdx.x; i < radix; i += kSortThreads) hs[(int64_t)i * tiles + t] = h[i];
+}
+
+__global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
+    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+    const int32_t *__restrict__ hist_scanned, SegInfo si, int shift, int digit_bits) {
+    __shared__ int cnt[kSortWarps][kSegMaxRadix];
+    const int radix = 1 << digit_bits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = lane; i < radix; i += 32) cnt[warp][i] = 0;
+    __syncwarp();
+    const int seg = seg_of_tile(si, blockIdx.x);
+    const int t = blockIdx.x - si.tile_base[seg];
+    const int tiles = si.tile_base[seg + 1] - si.tile_base[seg];
+    const int64_t end = si.seg_start[seg + 1];
+    const uint32_t kb = (uint32_t)si.key_base[seg];
+    const int64_t wbase = (int64_t)si.seg_start[seg] + (int64_t)t * kSortTile + (int64_t)warp * kSortWarpChunk;
+    uint32_t k[kSortRounds];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; r++) {
+        const int64_t idx = wbase + r * 32 + lane;
+        const bool valid = idx < end;
+        k[r] = valid ? keys_in[idx] : 0u;
+        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[warp][digit] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    const int32_t *hs = hist_scanned + (int64_t)radix * si.tile_base[seg];
+    for (int digit = threadIdx.x; digit < radix; digit += kSortThreads) {
+        int run = hs[(int64_t)digit * tiles + t];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            const int c = cnt[w][digit];
+            cnt[w][digit] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortRounds; r++) {
+        const int64_t idx = wbase + r * 32 + lane;
+        const bool valid = idx < end;
+        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        if (valid) {
+            const int pos = cnt[warp][digit] + rank;
+            keys_out[pos] = k[r];
+            vals_out[pos] = vals_in[idx];
+        }
+        __syncwarp();
+        if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                               const std::vector<int64_t> &seg_start, const int32_t *d_key_base,
+                               int local_bits, cudaStream_t s) {
+    const int S = (int)seg_start.size() - 1;
+    if (S <= 0 || seg_start[S] <= 0) return 0;
+    int passes = (local_bits + kSegMaxDigitBits - 1) / kSegMaxDigitBits;
+    if (passes < 1) passes = 1;
+    const int digit_bits = std::max(1, (local_bits + passes - 1) / passes);
+    const int radix = 1 << digit_bits;
+    std::vector<int32_t> h_seg(S + 1), h_tile(S + 1, 0);
+    for (int i = 0; i <= S; i++) h_seg[i] = (int32_t)seg_start[i];
+    for (int i = 0; i < S; i++) h_tile[i + 1] = h_tile[i] + ceil_div(seg_start[i + 1] - seg_start[i], kSortTile);
+    const int total_tiles = h_tile[S];
+    DevBuf<int32_t> d_seg, d_tile, hist;
+    d_seg.alloc(S + 1, s);
+    d_tile.alloc(S + 1, s);
+    DCRF_CUDA(cudaMemcpyAsync(d_seg.p, h_seg.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaMemcpyAsync(d_tile.p, h_tile.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
+    hist.alloc((size_t)radix * total_tiles + 1, s);
+    SegInfo si{d_seg.p, d_key_base, d_tile.p, S};
+    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    for (int p = 0; p < passes; p++) {
+        const int shift = p * digit_bits;
+        seg_radix_hist_kernel<<<total_tiles, kSortThreads, 0, s>>>(ki, hist.p, si, shift, digit_bits);
+        DCRF_LAUNCHED();
+        scan_rec(hist.p, hist.p, (int64_t)radix * total_tiles, false, s);
+        seg_radix_scatter_kernel<<<total_tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, hist.p, si, shift, digit_bits);
+        DCRF_LAUNCHED();
+        uint32_t *t;
+        t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    return passes & 1;
+}
+
+namespace {
+
 }  // namespace
 
 void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
     scan_rec(in, out, n, true, s);
 }
 
-void radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
-                      int64_t n, int bits, cudaStream_t s) {
-    if (n <= 0) return;
+int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                     int64_t n, int bits, cudaStream_t s) {
+    if (n <= 0) return 0;
     int passes = (bits + kRadixBits - 1) / kRadixBits;
     if (passes < 1) passes = 1;
-    if (passes & 1) passes++;  // even number of passes so that the result lands in *_a
     const int nb = ceil_div(n, kSortTile);
     DevBuf<int32_t> hist;
     hist.alloc((size_t)kRadix * nb + 1, s);
@@ -227,6 +375,7 @@ void radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint
         t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
     }
+    return passes & 1;
 }
 
 }  // namespace dcrf
