@@ -16,6 +16,36 @@ static thread_local std::string t_error;
 thread_local Profiler *t_prof = nullptr;
 void set_error(const std::string &msg) { t_error = msg; }
 
+namespace {
+struct ThreadPools {
+    cudaMemPool_t pool[64] = {};
+    ~ThreadPools() {
+        for (auto p : pool)
+            if (p) cudaMemPoolDestroy(p);
+    }
+};
+thread_local ThreadPools t_pools;
+}  // namespace
+
+cudaMemPool_t thread_pool() {
+    int dev = 0;
+    DCRF_CUDA(cudaGetDevice(&dev));
+    DCRF_REQUIRE(dev >= 0 && dev < 64, DCRF_EINVAL, "device index out of range");
+    if (!t_pools.pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached: every image needs fresh lattice buffers
+        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        t_pools.pool[dev] = pool;
+    }
+    return t_pools.pool[dev];
+}
+
 struct Pairwise {
     Lattice lat;
     DevBuf<float> norm;    // [Ntot]; empty for NO_NORMALIZATION
@@ -97,14 +127,6 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     std::unique_ptr<dcrf_handle> h(new dcrf_handle());
     h->device = device;
     DeviceGuard guard(device);
-    static std::atomic<uint64_t> pool_configured{0};
-    if (!(pool_configured.load() & (1ull << device))) {
-        cudaMemPool_t pool;
-        DCRF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t thr = UINT64_MAX;
-        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        pool_configured.fetch_or(1ull << device);
-    }
     if (stream) {
         h->stream = (cudaStream_t)stream;
     } else {

@@ -42,7 +42,12 @@ struct Error {
         DCRF_CUDA(cudaGetLastError());                 \
     } while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync pool: allocation is cheap after warm-up).
+// Memory pool of the calling host thread on the current device.  One pool per (thread, device):
+// host threads that drive different handles concurrently (pipelined batches) do not steal each
+// other's cached blocks, which would force the pools to re-grow (device-wide stalls) every batch.
+cudaMemPool_t thread_pool();
+
+// Stream-ordered device buffer (cudaMallocFromPoolAsync: allocation is cheap after warm-up).
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -60,7 +65,7 @@ struct DevBuf {
         release();
         s = stream;
         n = count;
-        if (count) DCRF_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), stream));
+        if (count) DCRF_CUDA(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), thread_pool(), stream));
     }
     void release() {
         if (p) cudaFreeAsync(p, s);
