@@ -125,3 +125,39 @@ def test_crf_inference_label_drop_in():
     srt = np.sort(Q, axis=0)
     decided = (srt[-1] - srt[-2]) > 1e-4
     assert (got == ref)[decided].all() and (got == ref).mean() >= 0.999
+
+
+def test_sharded_sweep_confusion_matches_oracle_pipeline():
+    """Config-5-style sweep on one GPU, emulating 2 ranks by running both shards and summing: the
+    int64 confusion must equal the single-shard run bit for bit, and equal a NumPy bincount over
+    the oracle's label maps wherever the oracle's argmax is decided."""
+    from oracle import oracle as O
+    from wsss_analysis_b200 import evaluation as E
+    from wsss_analysis_b200 import sweep
+
+    C_, n = 6, 5
+
+    def item(i):
+        img, U, gt = sweep.synthetic_item(i, C_)
+        return img[:90, :120].copy(), np.ascontiguousarray(U.reshape(C_, *gt.shape)[:, :90, :120].reshape(C_, -1)), gt[:90, :120].copy()
+
+    items = [item(i) for i in range(n)]
+    whole = sweep.run_sweep(items, C_, 0, 1, batch=3, all_reduce=False)
+    parts = [sweep.run_sweep(items, C_, r, 2, batch=2, all_reduce=False) for r in range(2)]
+    assert np.array_equal(whole["confusion"], parts[0]["confusion"] + parts[1]["confusion"])
+    assert whole["images"] == n and parts[0]["images"] + parts[1]["images"] == n
+    # oracle pipeline
+    ref = np.zeros((C_ + 1, C_), np.int64)
+    undecided = 0
+    for img, U, gt in items:
+        h, w = gt.shape
+        d = O.DenseCRF2D(w, h, C_)
+        d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=img, compat=10)
+        Q = d.inference(10)
+        srt = np.sort(Q, axis=0)
+        undecided += int(((srt[-1] - srt[-2]) <= 1e-4).sum())
+        ref += O.confusion(gt, Q.argmax(0), C_)
+    assert np.abs(whole["confusion"] - ref).sum() <= 2 * undecided
+    assert abs(whole["miou_irn"] - E.iou_irn(ref)[1]) < 1e-3

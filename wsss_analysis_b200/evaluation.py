@@ -54,6 +54,11 @@ class ConfusionAccumulator(object):
                                                        self.device.index, stream))
         return self
 
+    def synchronize(self):
+        import torch
+
+        torch.cuda.synchronize(self.device)
+
     def all_reduce(self, group=None):
         """Sum over all ranks (NCCL over NVLink on GPUs).  No-op without an initialised process group."""
         import torch.distributed as dist

@@ -75,13 +75,23 @@ def voc_like_sizes(n, seed=0):
     return [choices[i] for i in idx]
 
 
+def voc_like_size(i, seed=0):
+    """(W, H) of item i of a synthetic VOC-like list (independent of the list length)."""
+    choices = [(500, 375), (375, 500), (500, 333), (500, 500), (334, 500), (500, 334), (500, 374), (480, 360)]
+    rng = np.random.default_rng([seed, i, 15485863])
+    return choices[int(rng.integers(0, len(choices)))]
+
+
 def gt_map(H, W, C, seed=0, ignore=255, border=4):
     """int32 GT label map with blobs and an `ignore` border (VOC-style 255)."""
     from scipy import ndimage
 
     rng = np.random.default_rng(seed + 32452843)
-    z = np.stack([ndimage.gaussian_filter(rng.standard_normal((H, W)), sigma=min(H, W) / 10.0) for _ in range(C)])
-    gt = z.argmax(axis=0).astype(np.int32)
+    # blobs are drawn on a coarse grid (1/8 resolution) and upsampled by pixel replication
+    hc, wc = (H + 7) // 8, (W + 7) // 8
+    z = np.stack([ndimage.gaussian_filter(rng.standard_normal((hc, wc)), sigma=max(1.0, min(hc, wc) / 10.0))
+                  for _ in range(C)])
+    gt = np.kron(z.argmax(axis=0), np.ones((8, 8), np.int64))[:H, :W].astype(np.int32)
     gt[:border] = ignore
     gt[-border:] = ignore
     gt[:, :border] = ignore
