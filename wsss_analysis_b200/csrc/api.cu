@@ -73,6 +73,10 @@ struct dcrf_handle {
     bool exact = false;  // DCRF_OPT_EXACT_ARITHMETIC
     std::vector<std::unique_ptr<Pairwise>> pw;
     Profiler prof;
+    // side streams: the filters of all pairwise terms but the last run concurrently with the last
+    // one (the small, latency-bound Gaussian lattice hides behind the bandwidth-bound bilateral one)
+    cudaStream_t side[kMaxPairwise - 1] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxPairwise - 1] = {};
 };
 
 namespace {
@@ -181,12 +185,14 @@ const T *to_device(dcrf_handle *h, const T *src, size_t count, int on_device, De
 
 // splat + (d+1) blurs of pairwise k applied to `in` (pixel-major Lp); returns the blurred buffer
 const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int Lp, bool pre_norm,
-                               bool seq, float *bufA, float *bufB, bool fast = false) {
-    if (fast) launch_splat_fast(p.lat, in, bufA, Lp, h->stream);  // pre-norm folded into the weights
-    else launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, h->stream);
+                               bool seq, float *bufA, float *bufB, bool fast = false,
+                               cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
+    if (fast) launch_splat_fast(p.lat, in, bufA, Lp, st);  // pre-norm folded into the weights
+    else launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, st);
     float *cur = bufA, *nxt = bufB;
     for (int j = 0; j <= p.lat.d; j++) {
-        launch_blur(p.lat, j, cur, nxt, Lp, seq, h->stream);
+        launch_blur(p.lat, j, cur, nxt, Lp, seq, st);
         std::swap(cur, nxt);
     }
     return cur;
@@ -284,11 +290,30 @@ void step_inference(dcrf_handle *h) {
     memset(&a, 0, sizeof(a));
     a.seq = seq ? 1 : 0;
     a.fast = fast ? 1 : 0;
-    for (auto &p : h->pw) {
-        const float *blurred =
-            filter_to_lattice(h, *p, h->Q.p, h->Lp, pre_norm(p->ntype), seq, p->valA.p, p->valB.p, fast);
-        a.term[a.n_terms++] = make_term(*p, blurred);
+    const int n = (int)h->pw.size();
+    // per-kernel profiling wants serialised kernels; otherwise fork the first n-1 terms
+    const bool overlap = n >= 2 && !h->prof.on;
+    if (overlap) {
+        if (!h->ev_fork) {
+            DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            for (int k = 0; k < kMaxPairwise - 1; k++) {
+                DCRF_CUDA(cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking));
+                DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
+            }
+        }
+        DCRF_CUDA(cudaEventRecord(h->ev_fork, h->stream));
     }
+    for (int k = 0; k < n; k++) {
+        Pairwise &p = *h->pw[k];
+        cudaStream_t st = (overlap && k < n - 1) ? h->side[k] : h->stream;
+        if (st != h->stream) DCRF_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0));
+        const float *blurred =
+            filter_to_lattice(h, p, h->Q.p, h->Lp, pre_norm(p.ntype), seq, p.valA.p, p.valB.p, fast, st);
+        if (st != h->stream) DCRF_CUDA(cudaEventRecord(h->ev_join[k], st));
+        a.term[a.n_terms++] = make_term(p, blurred);
+    }
+    if (overlap)
+        for (int k = 0; k < n - 1; k++) DCRF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[k], 0));
     launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
 }
 
@@ -354,6 +379,15 @@ void dcrf_destroy(dcrf_t *h) {
         h->d_w.release();
         h->d_h.release();
         h->d_pix_start.release();
+        if (h->ev_fork) {
+            cudaStreamSynchronize(h->stream);
+            cudaEventDestroy(h->ev_fork);
+            for (int k = 0; k < kMaxPairwise - 1; k++) {
+                cudaStreamSynchronize(h->side[k]);
+                cudaStreamDestroy(h->side[k]);
+                cudaEventDestroy(h->ev_join[k]);
+            }
+        }
         if (h->own_stream) {
             cudaStreamSynchronize(h->stream);
             cudaStreamDestroy(h->stream);

@@ -560,12 +560,11 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const Slic
     const int gbase = lane - c;
     float mx = NEG;
     for (int i = 0; i < (int)g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
-    constexpr float kLog2e = 1.4426950408889634f;
     float4 e;
-    e.x = exp2f((t.x - mx) * kLog2e);  // exp2f(-inf) = 0 for the padding lanes
-    e.y = exp2f((t.y - mx) * kLog2e);
-    e.z = exp2f((t.z - mx) * kLog2e);
-    e.w = exp2f((t.w - mx) * kLog2e);
+    e.x = expf(t.x - mx);  // expf(-inf) = 0 for the padding lanes
+    e.y = expf(t.y - mx);
+    e.z = expf(t.z - mx);
+    e.w = expf(t.w - mx);
     const float ls = (e.x + e.y) + (e.z + e.w);
     float sum = 0.f;
     for (int i = 0; i < (int)g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
@@ -598,12 +597,11 @@ __global__ void __launch_bounds__(kThreads) softmax_unary_fast_kernel(const floa
     const int gbase = lane - c;
     float mx = NEG;
     for (int i = 0; i < (int)g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
-    constexpr float kLog2e = 1.4426950408889634f;
     float4 e;
-    e.x = exp2f((t.x - mx) * kLog2e);
-    e.y = exp2f((t.y - mx) * kLog2e);
-    e.z = exp2f((t.z - mx) * kLog2e);
-    e.w = exp2f((t.w - mx) * kLog2e);
+    e.x = expf(t.x - mx);
+    e.y = expf(t.y - mx);
+    e.z = expf(t.z - mx);
+    e.w = expf(t.w - mx);
     const float ls = (e.x + e.y) + (e.z + e.w);
     float sum = 0.f;
     for (int i = 0; i < (int)g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
