@@ -61,8 +61,14 @@ int64_t dcrf_launch_count(void);
 
 /* ---- construction --------------------------------------------------------------------------- */
 
+/* `stream` arguments: a cudaStream_t of the caller; NULL = the calling thread's persistent library
+ * stream (handles created by one thread then run in order on one stream); DCRF_STREAM_DEDICATED = a
+ * stream created for, and destroyed with, this handle (for callers that keep several handles of one
+ * thread in flight concurrently). */
+#define DCRF_STREAM_DEDICATED ((void *)(intptr_t)-1)
+
 /* Replaces `dcrf.DenseCRF2D(w, h, nlabels)` (03c_hsn/utilities.py:427; width first).
- * device < 0 = current device; stream = a cudaStream_t (NULL = the library creates its own). */
+ * device < 0 = current device. */
 int dcrf_create(int w, int h, int n_labels, int device, void *stream, dcrf_t **out);
 
 /* [EXT] `DenseCRF(nvar, nlabels)`: a model over n_vars variables without image geometry; only
@@ -82,7 +88,12 @@ void dcrf_destroy(dcrf_t *h);
  * folding of the normalisation into the splat weights): lattice values then match a sequential CPU
  * evaluation bit for bit, at roughly half the speed.  Default 0 (FMA / ex2.approx fast path; both
  * modes are run-to-run deterministic and within the 1e-4 tolerance on Q). */
-enum { DCRF_OPT_EXACT_ARITHMETIC = 1 };
+/* DCRF_OPT_ASYNC_HOST = 1: calls that read or write caller HOST buffers only enqueue their copies on
+ * the handle's stream and return; the caller keeps the buffers alive and untouched until
+ * dcrf_synchronize().  Lets one host thread keep two handles (two streams) in flight so that the
+ * PCIe copies of one batch overlap the kernels of the other (wsss_analysis_b200/pipeline.py).
+ * Host buffers should be page-locked, otherwise the copies are not asynchronous. */
+enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2 };
 int dcrf_set_option(dcrf_t *h, int option, int value);
 /* block the calling thread until everything enqueued on the handle's stream has finished */
 int dcrf_synchronize(dcrf_t *h);
@@ -118,6 +129,13 @@ int dcrf_inference(dcrf_t *h, int n_iter, float *Q_out, int on_device);
  * replaces `np.argmax(np.array(Q).reshape(L,H,W), axis=0)` (03c_hsn/utilities.py:443-444,
  * [EXT] crf_inference_label used by 03b_irn/step/cam_to_ir_label.py:35).  labels: sum(N_b) int32. */
 int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device);
+
+/* The two halves of dcrf_inference / dcrf_map, for callers that overlap the download of one batch
+ * with the iterations of the next (wsss_analysis_b200/pipeline.py): dcrf_run = startInference +
+ * n_iter steps, blocks until the iterations have finished; dcrf_get_q / dcrf_get_labels then emit the
+ * running Q (or its argmax). */
+int dcrf_run(dcrf_t *h, int n_iter);
+int dcrf_get_labels(dcrf_t *h, int32_t *labels_out, int on_device);
 
 /* [EXT] startInference / stepInference / klDivergence.  The running Q lives inside the handle. */
 int dcrf_start_inference(dcrf_t *h);

@@ -161,3 +161,38 @@ def test_sharded_sweep_confusion_matches_oracle_pipeline():
         ref += O.confusion(gt, Q.argmax(0), C_)
     assert np.abs(whole["confusion"] - ref).sum() <= 2 * undecided
     assert abs(whole["miou_irn"] - E.iou_irn(ref)[1]) < 1e-3
+
+
+def test_batch_pipeline_matches_blocking_calls():
+    """pipeline.BatchPipeline (async-host handles on dedicated streams) returns the same bits as the
+    blocking DenseCRFBatch calls, for marginals and for label maps."""
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200.pipeline import BatchPipeline, pinned_empty
+
+    cfg = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 40, "bi_srgb": 13, "bi_compat": 10, "iterations": 4}
+    L = 5
+    batches, ref = [], []
+    for k in range(5):
+        sizes = [(48 + 4 * k, 36), (40, 30 + k)]
+        imgs = [S.natural_image(h, w, 10 * k + i) for i, (w, h) in enumerate(sizes)]
+        Us = [S.random_unary(L, w * h, 10 * k + i) for i, (w, h) in enumerate(sizes)]
+        n = sum(w * h for w, h in sizes)
+        U = pinned_empty(n * L)
+        U[:] = np.concatenate([u.ravel() for u in Us])
+        I = pinned_empty(n * 3, np.uint8)
+        I[:] = np.concatenate([im.ravel() for im in imgs])
+        want_labels = k % 2 == 1
+        out = pinned_empty(n, np.int32) if want_labels else pinned_empty(n * L)
+        batches.append(dict(sizes=sizes, n_labels=L, unary=U, rgb=I, cfg=cfg, out=out, labels=want_labels))
+        d = G.DenseCRFBatch(sizes, L)
+        d.setUnaryEnergy(Us)
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs, compat=10)
+        ref.append(d.map(4) if want_labels else d.inference(4))
+    with BatchPipeline(n_slots=2) as pipe:
+        got = pipe.map(batches)
+    for g_, r_ in zip(got, ref):
+        assert len(g_) == len(r_)
+        for a, b in zip(g_, r_):
+            assert a.shape == b.shape and np.array_equal(a, b)

@@ -30,6 +30,8 @@ SIGNATURES = {
     "dcrf_add_pairwise_energy": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i]),
     "dcrf_inference": (_i, [_vp, _i, _vp, _i]),
     "dcrf_map": (_i, [_vp, _i, _vp, _i]),
+    "dcrf_run": (_i, [_vp, _i]),
+    "dcrf_get_labels": (_i, [_vp, _vp, _i]),
     "dcrf_start_inference": (_i, [_vp]),
     "dcrf_step_inference": (_i, [_vp]),
     "dcrf_get_q": (_i, [_vp, _vp, _i]),

@@ -2,7 +2,10 @@
 // mean-field loop.  One handle = a batch of independent images sharing L; all kernels run over the
 // concatenated pixel / vertex arrays of the batch on the handle's stream.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <memory>
@@ -25,7 +28,46 @@ struct ThreadPools {
     }
 };
 thread_local ThreadPools t_pools;
+
+// Persistent per-thread streams (main + side) per device: a handle created without a caller stream
+// runs on its creating thread's stream, so consecutive handles of a thread reuse the thread's pool
+// blocks in plain stream order and no stream is created / destroyed per image.
+struct ThreadStreams {
+    cudaStream_t main[64] = {};
+    cudaStream_t side[64][kMaxPairwise - 1] = {};
+    ~ThreadStreams() {
+        for (int d = 0; d < 64; d++) {
+            if (main[d]) cudaStreamDestroy(main[d]);
+            for (auto s : side[d])
+                if (s) cudaStreamDestroy(s);
+        }
+    }
+};
+thread_local ThreadStreams t_streams;
 }  // namespace
+
+static cudaStream_t thread_main_stream(int dev) {
+    if (!t_streams.main[dev]) DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.main[dev], cudaStreamNonBlocking));
+    return t_streams.main[dev];
+}
+static cudaStream_t thread_side_stream(int dev, int k) {
+    if (!t_streams.side[dev][k])
+        DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.side[dev][k], cudaStreamNonBlocking));
+    return t_streams.side[dev][k];
+}
+
+double trace_now() {
+    static const bool on = getenv("DCRF_TRACE") != nullptr;
+    if (!on) return 0.0;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+void trace_slow(const char *what, double t0, size_t bytes) {
+    if (t0 == 0.0) return;
+    const double dt = trace_now() - t0;
+    if (dt > 2.0) fprintf(stderr, "[dcrf trace] %s blocked %.1f ms (%zu bytes)\n", what, dt, bytes);
+}
 
 cudaMemPool_t thread_pool() {
     int dev = 0;
@@ -41,6 +83,11 @@ cudaMemPool_t thread_pool() {
         DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached: every image needs fresh lattice buffers
         DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        // Never let the allocator make one stream wait for another in order to recycle a block:
+        // with two handles of one thread in flight (pipeline.py) that silently serialises them.
+        // Blocks are recycled in stream order, or across streams once their free has completed.
+        int off = 0;
+        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
         t_pools.pool[dev] = pool;
     }
     return t_pools.pool[dev];
@@ -70,7 +117,8 @@ struct dcrf_handle {
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
     bool unary_set = false, q_valid = false;
-    bool exact = false;  // DCRF_OPT_EXACT_ARITHMETIC
+    bool exact = false;       // DCRF_OPT_EXACT_ARITHMETIC
+    bool async_host = false;  // DCRF_OPT_ASYNC_HOST
     std::vector<std::unique_ptr<Pairwise>> pw;
     Profiler prof;
     // side streams: the filters of all pairwise terms but the last run concurrently with the last
@@ -113,6 +161,11 @@ int guarded(F &&f) {
     }
 }
 
+// end of a call that read or wrote caller HOST memory: block unless the handle is in async-host mode
+void host_sync(dcrf_handle *h) {
+    if (!h->async_host) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+}
+
 int64_t total_ln(const dcrf_handle *h) { return h->geom.Ntot * (int64_t)h->L; }
 
 void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, int device, void *stream,
@@ -131,11 +184,13 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     std::unique_ptr<dcrf_handle> h(new dcrf_handle());
     h->device = device;
     DeviceGuard guard(device);
-    if (stream) {
-        h->stream = (cudaStream_t)stream;
-    } else {
+    if (stream == DCRF_STREAM_DEDICATED) {
         DCRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         h->own_stream = true;
+    } else if (stream) {
+        h->stream = (cudaStream_t)stream;
+    } else {
+        h->stream = thread_main_stream(device);  // persistent, owned by the calling thread
     }
     h->L = L;
     h->Lp = ((L + 3) / 4) * 4;
@@ -179,7 +234,9 @@ template <typename T>
 const T *to_device(dcrf_handle *h, const T *src, size_t count, int on_device, DevBuf<T> &stage) {
     if (on_device) return src;
     stage.alloc(count, h->stream);
+    const double t0 = trace_now();
     DCRF_CUDA(cudaMemcpyAsync(stage.p, src, sizeof(T) * count, cudaMemcpyHostToDevice, h->stream));
+    trace_slow("cudaMemcpyAsync H2D (enqueue)", t0, sizeof(T) * count);
     return stage.p;
 }
 
@@ -295,11 +352,13 @@ void step_inference(dcrf_handle *h) {
     const bool overlap = n >= 2 && !h->prof.on;
     if (overlap) {
         if (!h->ev_fork) {
+            const double t0 = trace_now();
             DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
             for (int k = 0; k < kMaxPairwise - 1; k++) {
-                DCRF_CUDA(cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking));
+                h->side[k] = thread_side_stream(h->device, k);
                 DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
             }
+            trace_slow("side stream/event creation", t0, 0);
         }
         DCRF_CUDA(cudaEventRecord(h->ev_fork, h->stream));
     }
@@ -327,7 +386,7 @@ void emit_q(dcrf_handle *h, float *Q_out, int on_device) {
         stage.alloc(n, h->stream);
         launch_pm_to_ln(h->Q.p, stage.p, h->geom, h->L, h->Lp, h->stream);
         DCRF_CUDA(cudaMemcpyAsync(Q_out, stage.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-        DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        host_sync(h);
     }
 }
 
@@ -373,6 +432,7 @@ void dcrf_destroy(dcrf_t *h) {
     if (!h) return;
     try {
         DeviceGuard guard(h->device);
+        const double t0 = trace_now();
         h->pw.clear();
         h->unary.release();
         h->Q.release();
@@ -382,16 +442,13 @@ void dcrf_destroy(dcrf_t *h) {
         if (h->ev_fork) {
             cudaStreamSynchronize(h->stream);
             cudaEventDestroy(h->ev_fork);
-            for (int k = 0; k < kMaxPairwise - 1; k++) {
-                cudaStreamSynchronize(h->side[k]);
-                cudaStreamDestroy(h->side[k]);
-                cudaEventDestroy(h->ev_join[k]);
-            }
+            for (int k = 0; k < kMaxPairwise - 1; k++) cudaEventDestroy(h->ev_join[k]);
         }
         if (h->own_stream) {
             cudaStreamSynchronize(h->stream);
             cudaStreamDestroy(h->stream);
         }
+        trace_slow("dcrf_destroy", t0, 0);
     } catch (...) {
     }
     delete h;
@@ -400,8 +457,10 @@ void dcrf_destroy(dcrf_t *h) {
 int dcrf_set_option(dcrf_t *h, int option, int value) {
     return guarded([&] {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
-        DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC, DCRF_EINVAL, "unknown option");
-        h->exact = value != 0;
+        DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC || option == DCRF_OPT_ASYNC_HOST, DCRF_EINVAL,
+                     "unknown option");
+        if (option == DCRF_OPT_EXACT_ARITHMETIC) h->exact = value != 0;
+        else h->async_host = value != 0;
     });
 }
 
@@ -420,7 +479,7 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
         DevBuf<float> stage;
         const float *src = to_device(h, U, (size_t)total_ln(h), on_device, stage);
         launch_ln_to_pm(src, h->unary.p, h->geom, h->L, h->Lp, h->stream);
-        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));  // caller may reuse U
+        if (!on_device) host_sync(h);  // caller may reuse U
         h->unary_set = true;
         h->q_valid = false;
     });
@@ -457,7 +516,7 @@ int dcrf_add_pairwise_bilateral(dcrf_t *h, float sx, float sy, float sr, float s
         fs.s[0] = sx; fs.s[1] = sy; fs.s[2] = sr; fs.s[3] = sg; fs.s[4] = sb;
         fs.rgb = to_device(h, rgb, (size_t)h->geom.Ntot * 3, on_device, stage);
         add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
-        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        if (!on_device) host_sync(h);
     });
 }
 
@@ -475,7 +534,7 @@ int dcrf_add_pairwise_energy(dcrf_t *h, const float *features, int d, int on_dev
         fs.d = d;
         fs.features = to_device(h, features, (size_t)h->geom.Ntot * d, on_device, stage);
         add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
-        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        if (!on_device) host_sync(h);
     });
 }
 
@@ -504,7 +563,35 @@ int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device) {
             launch_argmax(h->Q.p, stage.p, N, h->L, h->Lp, h->stream);
             DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost,
                                       h->stream));
-            DCRF_CUDA(cudaStreamSynchronize(h->stream));
+            host_sync(h);
+        }
+    });
+}
+
+int dcrf_run(dcrf_t *h, int n_iter) {
+    return guarded([&] {
+        DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
+        run_inference(h, n_iter);
+        host_sync(h);
+    });
+}
+
+int dcrf_get_labels(dcrf_t *h, int32_t *labels_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call dcrf_run / startInference first");
+        DeviceGuard guard(h->device);
+        const int64_t N = h->geom.Ntot;
+        if (on_device) {
+            launch_argmax(h->Q.p, labels_out, N, h->L, h->Lp, h->stream);
+        } else {
+            DevBuf<int32_t> stage;
+            stage.alloc(N, h->stream);
+            launch_argmax(h->Q.p, stage.p, N, h->L, h->Lp, h->stream);
+            DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, h->stream));
+            host_sync(h);
         }
     });
 }
@@ -543,7 +630,7 @@ int dcrf_set_q(dcrf_t *h, const float *Q_in, int on_device) {
         DevBuf<float> stage;
         const float *src = to_device(h, Q_in, (size_t)total_ln(h), on_device, stage);
         launch_ln_to_pm(src, h->Q.p, h->geom, h->L, h->Lp, h->stream);
-        if (!on_device) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        if (!on_device) host_sync(h);
         h->q_valid = true;
     });
 }

@@ -46,6 +46,9 @@ struct Error {
 // host threads that drive different handles concurrently (pipelined batches) do not steal each
 // other's cached blocks, which would force the pools to re-grow (device-wide stalls) every batch.
 cudaMemPool_t thread_pool();
+// DCRF_TRACE=1: report host-side CUDA calls that block for more than 2 ms (diagnostics)
+double trace_now();
+void trace_slow(const char *what, double t0, size_t bytes);
 
 // Stream-ordered device buffer (cudaMallocFromPoolAsync: allocation is cheap after warm-up).
 template <typename T>
@@ -65,7 +68,11 @@ struct DevBuf {
         release();
         s = stream;
         n = count;
-        if (count) DCRF_CUDA(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), thread_pool(), stream));
+        if (count) {
+            const double t0 = trace_now();
+            DCRF_CUDA(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), thread_pool(), stream));
+            trace_slow("cudaMallocFromPoolAsync", t0, count * sizeof(T));
+        }
     }
     void release() {
         if (p) cudaFreeAsync(p, s);

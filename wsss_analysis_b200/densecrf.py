@@ -86,7 +86,10 @@ class _Model(object):
         self._device = -1 if device is None else int(device)
         self._user_stream = stream
         self._stream_ptr = None
-        if stream is not None:
+        if isinstance(stream, str):
+            assert stream == "dedicated"
+            self._stream_ptr = C.c_void_p(-1).value  # DCRF_STREAM_DEDICATED
+        elif stream is not None:
             self._stream_ptr = int(getattr(stream, "cuda_stream", stream))
 
     # -- handle management --
@@ -110,6 +113,10 @@ class _Model(object):
             import torch
 
             torch.cuda.current_stream().synchronize()
+
+    def set_async_host(self, on=True):
+        """Host-buffer calls only enqueue their copies; call synchronize() before touching the buffers."""
+        _lib.check(self._lib.dcrf_set_option(self._h, 2, 1 if on else 0))
 
     def set_exact_arithmetic(self, on=True):
         """Use the specification's float association literally in the iteration kernels (slower)."""
@@ -415,10 +422,33 @@ class DenseCRFBatch(_Model):
         self.synchronize()
         return out
 
-    def map(self, niter):
-        """-> list of (H_b, W_b) int32 label maps."""
-        flat = np.empty(self._Ntot, np.int32)
+    def map(self, niter, out=None):
+        """-> list of (H_b, W_b) int32 label maps (views of `out` when given)."""
+        flat = np.empty(self._Ntot, np.int32) if out is None else out
+        assert flat.dtype == np.int32 and flat.size == self._Ntot and flat.flags.c_contiguous
+        flat = flat.reshape(-1)
         _lib.check(self._lib.dcrf_map(self._h, int(niter), flat.ctypes.data, 0))
+        return self._split(flat, 1, lambda b: (self._sizes[b][1], self._sizes[b][0]))
+
+    # -- split form of inference()/map(): iterate now, download later (pipeline.py) --
+    def run(self, niter):
+        """startInference + niter steps; the running Q stays inside the handle."""
+        _lib.check(self._lib.dcrf_run(self._h, int(niter)))
+
+    def marginals(self, out=None):
+        """Download the running Q -> list of (L, N_b) float32 arrays (views of `out` when given)."""
+        flat = np.empty(self._Ntot * self._L, np.float32) if out is None else out
+        assert flat.dtype == np.float32 and flat.size == self._Ntot * self._L and flat.flags.c_contiguous
+        flat = flat.reshape(-1)
+        _lib.check(self._lib.dcrf_get_q(self._h, flat.ctypes.data, 0))
+        return self._split(flat, self._L, lambda b: (self._L, int(self._npix[b])))
+
+    def labels(self, out=None):
+        """Download argmax of the running Q -> list of (H_b, W_b) int32 label maps."""
+        flat = np.empty(self._Ntot, np.int32) if out is None else out
+        assert flat.dtype == np.int32 and flat.size == self._Ntot and flat.flags.c_contiguous
+        flat = flat.reshape(-1)
+        _lib.check(self._lib.dcrf_get_labels(self._h, flat.ctypes.data, 0))
         return self._split(flat, 1, lambda b: (self._sizes[b][1], self._sizes[b][0]))
 
     def startInference(self):
