@@ -235,7 +235,7 @@ def run_ours(args):
     # batch pays its own H2D of unaries + image and its own D2H of Q inside the timed region.
     from wsss_analysis_b200.pipeline import BatchPipeline
 
-    n_slots = int(os.environ.get("BENCH_SLOTS", "2"))
+    n_slots = int(os.environ.get("BENCH_SLOTS", "3"))
     slot_Q = [Q_host] + [torch.empty_like(Q_host).pin_memory() for _ in range(n_slots - 1)]
     crf_cfg = {"g_sxy": G_SXY, "g_compat": G_COMPAT, "bi_sxy": B_SXY, "bi_srgb": B_SRGB, "bi_compat": B_COMPAT,
                "iterations": N_ITER}

@@ -67,6 +67,12 @@ int64_t dcrf_launch_count(void);
  * thread in flight concurrently). */
 #define DCRF_STREAM_DEDICATED ((void *)(intptr_t)-1)
 
+/* Long-lived streams for callers that keep several handles in flight (pipeline.py) without
+ * depending on PyTorch for stream objects.  The library keeps one device-memory pool per stream;
+ * dcrf_stream_destroy also releases that pool. */
+int dcrf_stream_create(int device, void **stream_out);
+int dcrf_stream_destroy(void *stream);
+
 /* Replaces `dcrf.DenseCRF2D(w, h, nlabels)` (03c_hsn/utilities.py:427; width first).
  * device < 0 = current device. */
 int dcrf_create(int w, int h, int n_labels, int device, void *stream, dcrf_t **out);

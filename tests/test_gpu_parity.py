@@ -259,3 +259,31 @@ def test_confusion_bit_exact(mods):
     valid = (m >= 0) & (m < C_)
     ref2 = np.bincount(C_ * m[valid] + pred[valid], minlength=C_ * C_).reshape(C_, C_)
     assert np.array_equal(conf[:C_], ref2)
+
+
+def test_uniform_batch_shares_the_gaussian_lattice(mods):
+    """All images of one size: the position-only lattice is built once and replicated; every image
+    must still export exactly the oracle's lattice, and Q must match image by image."""
+    O, G, S = mods
+    sizes = [(60, 44)] * 5
+    L = 7
+    imgs = [S.natural_image(h, w, 30 + i) for i, (w, h) in enumerate(sizes)]
+    Us = [S.random_unary(L, w * h, 30 + i) for i, (w, h) in enumerate(sizes)]
+    gb = G.DenseCRFBatch(sizes, L)
+    gb.setUnaryEnergy(Us)
+    gb.addPairwiseGaussian(sxy=3, compat=3)
+    gb.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs, compat=10)
+    Qb = gb.inference(5)
+    for i, (w, h) in enumerate(sizes):
+        o = O.DenseCRF2D(w, h, L)
+        o.setUnaryEnergy(Us[i])
+        o.addPairwiseGaussian(sxy=3, compat=3)
+        o.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs[i], compat=10)
+        for k in range(2):
+            eo, eg = o.lattice(k), gb.lattice_export(k, image=i)
+            assert eo.M == eg["M"]
+            assert np.array_equal(eo.keys, eg["keys"]) and np.array_equal(eo.offsets, eg["offsets"])
+            assert np.array_equal(eo.neighbours, eg["neighbours"])
+            assert np.array_equal(eo.bary.view(np.uint32), eg["bary"].view(np.uint32))
+            np.testing.assert_allclose(eg["norm"], o.norm(k), rtol=2e-6, atol=0)
+        assert np.abs(o.inference(5) - Qb[i]).max() <= Q_TOL

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -20,15 +22,6 @@ thread_local Profiler *t_prof = nullptr;
 void set_error(const std::string &msg) { t_error = msg; }
 
 namespace {
-struct ThreadPools {
-    cudaMemPool_t pool[64] = {};
-    ~ThreadPools() {
-        for (auto p : pool)
-            if (p) cudaMemPoolDestroy(p);
-    }
-};
-thread_local ThreadPools t_pools;
-
 // Persistent per-thread streams (main + side) per device: a handle created without a caller stream
 // runs on its creating thread's stream, so consecutive handles of a thread reuse the thread's pool
 // blocks in plain stream order and no stream is created / destroyed per image.
@@ -69,28 +62,34 @@ void trace_slow(const char *what, double t0, size_t bytes) {
     if (dt > 2.0) fprintf(stderr, "[dcrf trace] %s blocked %.1f ms (%zu bytes)\n", what, dt, bytes);
 }
 
-cudaMemPool_t thread_pool() {
+static std::mutex g_pool_mu;
+static std::unordered_map<cudaStream_t, cudaMemPool_t> g_pools;
+
+cudaMemPool_t stream_pool(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pools.find(stream);
+    if (it != g_pools.end()) return it->second;
     int dev = 0;
     DCRF_CUDA(cudaGetDevice(&dev));
-    DCRF_REQUIRE(dev >= 0 && dev < 64, DCRF_EINVAL, "device index out of range");
-    if (!t_pools.pool[dev]) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        cudaMemPool_t pool;
-        DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
-        uint64_t thr = UINT64_MAX;  // keep freed blocks cached: every image needs fresh lattice buffers
-        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        // Never let the allocator make one stream wait for another in order to recycle a block:
-        // with two handles of one thread in flight (pipeline.py) that silently serialises them.
-        // Blocks are recycled in stream order, or across streams once their free has completed.
-        int off = 0;
-        DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
-        t_pools.pool[dev] = pool;
-    }
-    return t_pools.pool[dev];
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
+    uint64_t thr = UINT64_MAX;  // keep freed blocks cached: every image needs fresh lattice buffers
+    DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    g_pools[stream] = pool;
+    return pool;
+}
+
+void stream_pool_release(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pools.find(stream);
+    if (it == g_pools.end()) return;
+    cudaMemPoolDestroy(it->second);
+    g_pools.erase(it);
 }
 
 struct Pairwise {
@@ -292,21 +291,49 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         DCRF_CUDA(cudaMemcpyAsync(p->compat.p, c.data(), sizeof(float) * Lp * Lp, cudaMemcpyHostToDevice, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     }
-    build_lattice(h->geom, fs, p->lat, s);
+    // A lattice whose features depend on the pixel position only (the Gaussian kernel) is the same
+    // for every image of a given size: when all images of the batch have one size it is built (and
+    // its norm filtered) ONCE for a single image and replicated with per-image id offsets.
+    bool uniform = fs.mode == 0 && h->geom.B > 1;
+    for (int b = 1; uniform && b < h->geom.B; b++)
+        uniform = h->geom.w[b] == h->geom.w[0] && h->geom.h[b] == h->geom.h[0];
+    BatchGeom one = h->geom;
+    if (uniform) {
+        one.B = 1;
+        one.Ntot = h->geom.pix_start[1];
+        one.w.resize(1);
+        one.h.resize(1);
+        one.pix_start.resize(2);  // device arrays are shared: their first entries describe image 0
+    }
+    const BatchGeom &bg = uniform ? one : h->geom;
+    Lattice single;
+    Lattice &lat = uniform ? single : p->lat;
+    DevBuf<float> norm_single;
+    DevBuf<float> &norm = uniform ? norm_single : p->norm;
+    build_lattice(bg, fs, lat, s);
     // A.5: norm = filter(ones) through the value_size = 1 path
     if (ntype != DCRF_NO_NORMALIZATION) {
         DevBuf<float> ones, a, b, sliced;
-        ones.alloc((size_t)Ntot * 4, s);
-        a.alloc((size_t)p->lat.M * 4, s);
-        b.alloc((size_t)p->lat.M * 4, s);
-        sliced.alloc((size_t)Ntot * 4, s);
-        launch_fill_ones_col0(ones.p, Ntot, 4, s);
-        const float *blurred = filter_to_lattice(h, *p, ones.p, 4, false, true, a.p, b.p);
-        launch_slice_plain(p->lat, blurred, sliced.p, Ntot, 4, true, s);
-        p->norm.alloc(Ntot, s);
-        launch_norm_finalize(sliced.p, 4, p->norm.p, Ntot, ntype, s);
+        ones.alloc((size_t)bg.Ntot * 4, s);
+        a.alloc((size_t)lat.M * 4, s);
+        b.alloc((size_t)lat.M * 4, s);
+        sliced.alloc((size_t)bg.Ntot * 4, s);
+        launch_fill_ones_col0(ones.p, bg.Ntot, 4, s);
+        launch_splat(lat, ones.p, nullptr, a.p, 4, s);
+        float *cur = a.p, *nxt = b.p;
+        for (int j = 0; j <= lat.d; j++) {
+            launch_blur(lat, j, cur, nxt, 4, true, s);
+            std::swap(cur, nxt);
+        }
+        launch_slice_plain(lat, cur, sliced.p, bg.Ntot, 4, true, s);
+        norm.alloc(bg.Ntot, s);
+        launch_norm_finalize(sliced.p, 4, norm.p, bg.Ntot, ntype, s);
     }
-    launch_pack_fast_tables(p->lat, pre_norm(ntype) ? p->norm.p : nullptr, s);
+    launch_pack_fast_tables(lat, pre_norm(ntype) ? norm.p : nullptr, s);
+    if (uniform) {
+        if (norm.p) p->norm.alloc(Ntot, s);
+        launch_replicate_lattice(single, norm.p, h->geom.B, bg.Ntot, p->lat, p->norm.p, s);
+    }
     p->valA.alloc((size_t)p->lat.M * Lp, s);
     p->valB.alloc((size_t)p->lat.M * Lp, s);
     h->pw.push_back(std::move(p));
@@ -446,12 +473,37 @@ void dcrf_destroy(dcrf_t *h) {
         }
         if (h->own_stream) {
             cudaStreamSynchronize(h->stream);
+            stream_pool_release(h->stream);
             cudaStreamDestroy(h->stream);
         }
         trace_slow("dcrf_destroy", t0, 0);
     } catch (...) {
     }
     delete h;
+}
+
+int dcrf_stream_create(int device, void **stream_out) {
+    return guarded([&] {
+        DCRF_REQUIRE(stream_out, DCRF_EINVAL, "NULL argument");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw Error{DCRF_ECUDA, "no CUDA device: dcrf_b200 has no CPU fallback"};
+        if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
+        DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
+        DeviceGuard guard(device);
+        cudaStream_t s;
+        DCRF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        *stream_out = (void *)s;
+    });
+}
+
+int dcrf_stream_destroy(void *stream) {
+    return guarded([&] {
+        DCRF_REQUIRE(stream, DCRF_EINVAL, "NULL stream");
+        DCRF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        stream_pool_release((cudaStream_t)stream);
+        DCRF_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    });
 }
 
 int dcrf_set_option(dcrf_t *h, int option, int value) {

@@ -42,10 +42,13 @@ struct Error {
         DCRF_CUDA(cudaGetLastError());                 \
     } while (0)
 
-// Memory pool of the calling host thread on the current device.  One pool per (thread, device):
-// host threads that drive different handles concurrently (pipelined batches) do not steal each
-// other's cached blocks, which would force the pools to re-grow (device-wide stalls) every batch.
-cudaMemPool_t thread_pool();
+// One memory pool PER STREAM (created on first use, destroyed with dcrf_stream_destroy or at exit).
+// Every block is then allocated, freed and recycled in the order of ONE stream: no cross-stream
+// reuse, hence no hidden inter-stream dependencies and no pool growth after the first batches.
+// (A shared pool re-grows whenever a block freed on another stream is still in flight, and growing
+// a pool maps device memory, which stalls for 10-600 ms when the GPU is busy -- measured.)
+cudaMemPool_t stream_pool(cudaStream_t stream);
+void stream_pool_release(cudaStream_t stream);
 // DCRF_TRACE=1: report host-side CUDA calls that block for more than 2 ms (diagnostics)
 double trace_now();
 void trace_slow(const char *what, double t0, size_t bytes);
@@ -70,7 +73,7 @@ struct DevBuf {
         n = count;
         if (count) {
             const double t0 = trace_now();
-            DCRF_CUDA(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), thread_pool(), stream));
+            DCRF_CUDA(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), stream_pool(stream), stream));
             trace_slow("cudaMallocFromPoolAsync", t0, count * sizeof(T));
         }
     }
@@ -161,6 +164,10 @@ struct Lattice {
 };
 
 void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
+// `one` (lattice of a single image with n_img pixels, fast tables packed) -> `out`: the same lattice
+// for B identical images laid back to back, ids shifted per image (b * M, b * n_img, b * E).
+void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, int64_t n_img, Lattice &out,
+                              float *norm_out, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // filtering + mean field (filter.cu)

@@ -503,4 +503,102 @@ void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaS
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// replication of a geometry-only lattice over the B identical images of a batch
+// ---------------------------------------------------------------------------------------------
+namespace {
+// grid (ceil(n / 256), B): out[b * n + i] = in[i] (+ b * shift when in[i] >= 0)
+__global__ void __launch_bounds__(kThreads) rep_i32_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                           int64_t n, int64_t shift) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = in[i];
+    out[(int64_t)blockIdx.y * n + i] = v >= 0 ? (int32_t)(v + (int64_t)blockIdx.y * shift) : v;
+}
+// pairs (id, payload): x shifted, y copied
+__global__ void __launch_bounds__(kThreads) rep_i2_kernel(const int2 *__restrict__ in, int2 *__restrict__ out,
+                                                          int64_t n, int64_t shift_x, int64_t shift_y) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    int2 v = in[i];
+    if (v.x >= 0) v.x = (int32_t)(v.x + (int64_t)blockIdx.y * shift_x);
+    if (shift_y && v.y >= 0) v.y = (int32_t)(v.y + (int64_t)blockIdx.y * shift_y);
+    out[(int64_t)blockIdx.y * n + i] = v;
+}
+__global__ void __launch_bounds__(kThreads) rep_f32_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                           int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) out[(int64_t)blockIdx.y * n + i] = in[i];
+}
+__global__ void __launch_bounds__(kThreads) rep_i4_kernel(const int4 *__restrict__ in, int4 *__restrict__ out,
+                                                          int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) out[(int64_t)blockIdx.y * n + i] = in[i];
+}
+// neighbour table is [axis][vertex]: out[(j * B*M) + b*M + v]
+__global__ void __launch_bounds__(kThreads) rep_neigh_kernel(const int2 *__restrict__ in, int2 *__restrict__ out,
+                                                             int64_t M, int B, int d1) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= M * d1) return;
+    const int j = (int)(i / M);
+    const int64_t v = i - (int64_t)j * M;
+    int2 nb = in[i];
+    const int64_t sh = (int64_t)blockIdx.y * M;
+    if (nb.x >= 0) nb.x = (int32_t)(nb.x + sh);
+    if (nb.y >= 0) nb.y = (int32_t)(nb.y + sh);
+    out[(int64_t)j * M * B + sh + v] = nb;
+}
+}  // namespace
+
+void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, int64_t n_img, Lattice &out,
+                              float *norm_out, cudaStream_t s) {
+    const int d1 = one.d + 1;
+    const int64_t M = one.M, E = one.E;
+    DCRF_REQUIRE(E * B < (int64_t)2147483000, DCRF_EINVAL, "batch too large: N*(d+1) must stay below 2^31");
+    out.d = one.d;
+    out.M = M * B;
+    out.E = E * B;
+    out.vert_start.resize(B + 1);
+    for (int b = 0; b <= B; b++) out.vert_start[b] = M * b;
+    out.offset.alloc(out.E, s);
+    out.bary.alloc(out.E, s);
+    out.neigh.alloc((size_t)out.M * d1, s);
+    out.vkeys.alloc((size_t)out.M * 8, s);
+    out.csr_start.alloc(out.M + 1, s);
+    out.csr_pix.alloc(out.E, s);
+    out.csr_w.alloc(out.E, s);
+    out.ent.alloc(out.E, s);
+    out.csr_ent.alloc(out.E, s);
+    auto grid = [&](int64_t n) { return dim3(ceil_div(n, kThreads), B); };
+    rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.offset.p, out.offset.p, E, M);
+    DCRF_LAUNCHED();
+    rep_f32_kernel<<<grid(E), kThreads, 0, s>>>(one.bary.p, out.bary.p, E);
+    DCRF_LAUNCHED();
+    rep_neigh_kernel<<<grid(M * d1), kThreads, 0, s>>>(one.neigh.p, out.neigh.p, M, B, d1);
+    DCRF_LAUNCHED();
+    rep_i4_kernel<<<grid(M), kThreads, 0, s>>>(reinterpret_cast<const int4 *>(one.vkeys.p),
+                                                reinterpret_cast<int4 *>(out.vkeys.p), M);
+    DCRF_LAUNCHED();
+    // csr_start has M+1 entries per image; entry M of image b coincides with entry 0 of image b+1
+    rep_i32_kernel<<<grid(M), kThreads, 0, s>>>(one.csr_start.p, out.csr_start.p, M, E);
+    DCRF_LAUNCHED();
+    const int32_t total = (int32_t)out.E;
+    DCRF_CUDA(cudaMemcpyAsync(out.csr_start.p + out.M, &total, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaStreamSynchronize(s));  // `total` is a stack variable
+    rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_pix.p, out.csr_pix.p, E, n_img);
+    DCRF_LAUNCHED();
+    rep_f32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_w.p, out.csr_w.p, E);
+    DCRF_LAUNCHED();
+    rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.ent.p, out.ent.p, E, M, 0);
+    DCRF_LAUNCHED();
+    rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, E, n_img, 0);
+    DCRF_LAUNCHED();
+    if (one.row_counter.p) out.row_counter.alloc(1, s);
+    if (norm_one && norm_out) {
+        rep_f32_kernel<<<grid(n_img), kThreads, 0, s>>>(norm_one, norm_out, n_img);
+        DCRF_LAUNCHED();
+    }
+}
+
 }  // namespace dcrf

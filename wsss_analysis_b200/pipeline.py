@@ -5,25 +5,35 @@ The reference drives the CRF from plain loops over host NumPy arrays
 (/root/reference/03c_hsn/utilities.py:424, 03a_sec-dsrg/model.py:665).  A batch whose inputs and
 outputs live in host memory costs two PCIe transfers (unaries in, marginals out) around the GPU work;
 run back to back they leave the GPU idle a third of the time.  Here every batch gets its own handle on
-a dedicated stream in async-host mode (`DCRF_OPT_ASYNC_HOST`): its H2D copy, lattice build, iterations
+a long-lived per-slot stream in async-host mode (`DCRF_OPT_ASYNC_HOST`): its H2D copy, lattice build, iterations
 and D2H copy are only enqueued, and the host moves on to the next batch while the previous one is
 still computing / downloading.  (Driving the handles from several host threads instead makes the
 threads collide inside the CUDA driver's allocator locks -- measured)
 All calls go through the C ABI with host pointers (`on_device = 0`); host buffers should be
 page-locked (`pinned_empty`).
 """
+import ctypes as C
+
 import numpy as np
 
+from . import _lib
 from .densecrf import DenseCRFBatch
 
 
 class BatchPipeline(object):
-    def __init__(self, n_slots=2, device=None):
+    def __init__(self, n_slots=3, device=None):
         self.n_slots = int(n_slots)
         self.device = device
         self._slots = [None] * self.n_slots   # (handle, result views, ticket)
         self._next = 0
         self._done = {}
+        # one long-lived stream (and therefore one device-memory pool) per slot
+        self._lib = _lib.load()
+        self._streams = []
+        for _ in range(self.n_slots):
+            s = C.c_void_p()
+            _lib.check(self._lib.dcrf_stream_create(-1 if device is None else int(device), C.byref(s)))
+            self._streams.append(s.value)
 
     def _finish(self, slot):
         if self._slots[slot] is None:
@@ -41,7 +51,7 @@ class BatchPipeline(object):
         slot = ticket % self.n_slots
         self._next += 1
         self._finish(slot)
-        crf = DenseCRFBatch(sizes, n_labels, device=self.device, stream="dedicated")
+        crf = DenseCRFBatch(sizes, n_labels, device=self.device, stream=self._streams[slot])
         crf.set_async_host(True)
         crf.setUnaryEnergy(unary)
         crf.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
@@ -64,6 +74,9 @@ class BatchPipeline(object):
     def close(self):
         for s in range(self.n_slots):
             self._finish(s)
+        for st in self._streams:
+            self._lib.dcrf_stream_destroy(st)
+        self._streams = []
 
     def __enter__(self):
         return self
