@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdcrf_b200.so")
+LIB_PATH = os.environ.get("DCRF_B200_LIB") or os.path.join(_HERE, "csrc", "libdcrf_b200.so")  # env override: tuning builds
 
 DCRF_OK, DCRF_EINVAL, DCRF_ECUDA, DCRF_ESTATE, DCRF_ENOMEM = 0, 1, 2, 3, 4
 
