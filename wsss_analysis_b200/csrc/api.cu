@@ -313,21 +313,8 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
     build_lattice(bg, fs, lat, s);
     // A.5: norm = filter(ones) through the value_size = 1 path
     if (ntype != DCRF_NO_NORMALIZATION) {
-        DevBuf<float> ones, a, b, sliced;
-        ones.alloc((size_t)bg.Ntot * 4, s);
-        a.alloc((size_t)lat.M * 4, s);
-        b.alloc((size_t)lat.M * 4, s);
-        sliced.alloc((size_t)bg.Ntot * 4, s);
-        launch_fill_ones_col0(ones.p, bg.Ntot, 4, s);
-        launch_splat(lat, ones.p, nullptr, a.p, 4, s);
-        float *cur = a.p, *nxt = b.p;
-        for (int j = 0; j <= lat.d; j++) {
-            launch_blur(lat, j, cur, nxt, 4, true, s);
-            std::swap(cur, nxt);
-        }
-        launch_slice_plain(lat, cur, sliced.p, bg.Ntot, 4, true, s);
         norm.alloc(bg.Ntot, s);
-        launch_norm_finalize(sliced.p, 4, norm.p, bg.Ntot, ntype, s);
+        launch_kernel_norm(lat, bg.Ntot, ntype, norm.p, s);
     }
     launch_pack_fast_tables(lat, pre_norm(ntype) ? norm.p : nullptr, s);
     if (uniform) {

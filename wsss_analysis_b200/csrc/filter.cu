@@ -642,6 +642,46 @@ __global__ void __launch_bounds__(kThreads) slice_pairwise_kernel(const SliceTer
     if (act) st4(out + (p * g + c) * 4, y);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kernel normalisation (A.5): norm = f( filter(all-ones) ) through the value_size = 1 association
+// of A.4 (splat w * 1, blur through a double 0.5, slice (w * v) * alpha).  Scalar kernels: one float
+// per vertex / pixel instead of a padded float4 row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) norm_splat_kernel(const int32_t *__restrict__ csr_start,
+                                                              const float *__restrict__ csr_w,
+                                                              float *__restrict__ val, int64_t M) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= M) return;
+    float acc = 0.f;
+    const int s1 = csr_start[v + 1];
+    for (int s = csr_start[v]; s < s1; s++) acc = __fadd_rn(acc, __fmul_rn(csr_w[s], 1.0f));
+    val[v] = acc;
+}
+__global__ void __launch_bounds__(kThreads) norm_blur_kernel(const int2 *__restrict__ neigh,
+                                                             const float *__restrict__ in,
+                                                             float *__restrict__ out, int64_t M) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= M) return;
+    const int2 nb = neigh[v];
+    const float a = nb.x >= 0 ? in[nb.x] : 0.f, b = nb.y >= 0 ? in[nb.y] : 0.f;
+    out[v] = (float)((double)in[v] + 0.5 * (double)__fadd_rn(a, b));
+}
+__global__ void __launch_bounds__(kThreads) norm_slice_kernel(const int32_t *__restrict__ offset,
+                                                              const float *__restrict__ bary,
+                                                              const float *__restrict__ val, int d, float alpha,
+                                                              float *__restrict__ norm, int64_t N, int ntype) {
+    const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= N) return;
+    float acc = 0.f;
+    const int64_t base = p * (d + 1);
+    for (int r = 0; r <= d; r++)
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(bary[base + r], val[offset[base + r]]), alpha));
+    float res;
+    if (ntype == DCRF_NORMALIZE_SYMMETRIC) res = (float)(1.0 / sqrt((double)acc + 1e-20));
+    else res = (float)(1.0 / ((double)acc + 1e-20));
+    norm[p] = res;
+}
+
 // norm[p] from the sliced all-ones filter (column 0 of an Lp-wide buffer)      (A.5)
 __global__ void __launch_bounds__(kThreads) norm_finalize_kernel(const float *__restrict__ sliced,
                                                                  int Lp, float *__restrict__ norm,
@@ -949,6 +989,26 @@ void launch_norm_finalize(const float *sliced, int Lp, float *norm, int64_t Ntot
                           cudaStream_t s) {
     if (Ntot == 0) return;
     norm_finalize_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(sliced, Lp, norm, Ntot, ntype);
+    DCRF_LAUNCHED();
+}
+
+void launch_kernel_norm(const Lattice &lat, int64_t N, int ntype, float *norm, cudaStream_t s) {
+    if (N == 0 || lat.M == 0) return;
+    DevBuf<float> a, b;
+    a.alloc(lat.M, s);
+    b.alloc(lat.M, s);
+    const int nbm = ceil_div(lat.M, kThreads);
+    norm_splat_kernel<<<nbm, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_w.p, a.p, lat.M);
+    DCRF_LAUNCHED();
+    float *cur = a.p, *nxt = b.p;
+    for (int j = 0; j <= lat.d; j++) {
+        norm_blur_kernel<<<nbm, kThreads, 0, s>>>(lat.neigh.p + (int64_t)j * lat.M, cur, nxt, lat.M);
+        DCRF_LAUNCHED();
+        std::swap(cur, nxt);
+    }
+    const float alpha = 1.0f / (1.0f + powf(2.0f, (float)-lat.d));
+    norm_slice_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(lat.offset.p, lat.bary.p, cur, lat.d, alpha, norm,
+                                                              N, ntype);
     DCRF_LAUNCHED();
 }
 

@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
     const int32_t *__restrict__ slot_of, const int32_t *__restrict__ scanned,
     const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
-    int32_t *__restrict__ offset, int32_t *__restrict__ vert_rep, int4 *__restrict__ vkeys) {
+    int32_t *__restrict__ offset, int32_t *__restrict__ vert_rep, int4 *__restrict__ vkeys,
+    uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals) {
     const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (e >= E) return;
     const int64_t gp = e / (D + 1);
@@ -278,6 +279,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     const int32_t rep = table[tab_start[b] + slot_of[e]];
     const int32_t id = scanned[rep];
     offset[e] = id;
+    sort_keys[e] = (uint32_t)id;  // (vertex, entry) pairs for the CSR sort (K6)
+    sort_vals[e] = (uint32_t)e;
     if (rep == (int32_t)e) {
         vert_rep[id] = (int32_t)e;
         short key[8];
@@ -305,7 +308,10 @@ __global__ void vert_start_kernel(const int *__restrict__ pix_start, int B, int 
     if (b <= B) vert_start[b] = scanned[(int64_t)pix_start[b] * d1];
 }
 
-// K5: neighbours.  One thread per (axis j, vertex v); table now holds vertex ids.
+// K5: neighbours.  One thread per (axis j, vertex v); table now holds vertex ids.  Only the first
+// neighbour n1 = key + (-1,..,+d at j,..,-1) is looked up: the relation is mutual (n2 of u is v iff
+// n1 of v is u), so the thread also stores itself as the second neighbour of the vertex it found.
+// neigh[] is pre-filled with -1; every int is written by at most one thread.
 template <int D>
 __global__ void __launch_bounds__(kThreads) neighbour_kernel(
     int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
@@ -320,41 +326,24 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(
     const uint32_t mask = (uint32_t)tab_mask[b];
     const int4 kv = vkeys[v];
     const short *key = reinterpret_cast<const short *>(&kv);
-    int res[2];
+    short nk[8];
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-        short nk[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k < D) {
-                int delta = (side == 0) ? -1 : 1;
-                if (k == j) delta = (side == 0) ? D : -D;
-                nk[k] = (short)(key[k] + delta);
-            } else {
-                nk[k] = 0;
-            }
-        }
-        const int4 pk = pack_key(nk);
-        uint32_t h = key_hash(pk) & mask;
-        int found = -1;
-        for (;;) {
-            int32_t cur = tab[h];
-            if (cur < 0) break;
-            if (key_eq(vkeys[cur], pk)) { found = cur; break; }
-            h = (h + 1) & mask;
-        }
-        res[side] = found;
+    for (int k = 0; k < 8; k++) {
+        if (k < D) nk[k] = (short)(key[k] + ((k == j) ? D : -1));
+        else nk[k] = 0;
     }
-    neigh[(int64_t)j * M + v] = make_int2(res[0], res[1]);
-}
-
-__global__ void __launch_bounds__(kThreads) iota_copy_kernel(const int32_t *__restrict__ offset,
-                                                             uint32_t *__restrict__ keys,
-                                                             uint32_t *__restrict__ vals, int64_t E) {
-    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= E) return;
-    keys[e] = (uint32_t)offset[e];
-    vals[e] = (uint32_t)e;
+    const int4 pk = pack_key(nk);
+    uint32_t h = key_hash(pk) & mask;
+    int found = -1;
+    for (;;) {
+        const int32_t cur = tab[h];
+        if (cur < 0) break;
+        if (key_eq(vkeys[cur], pk)) { found = cur; break; }
+        h = (h + 1) & mask;
+    }
+    int *nflat = reinterpret_cast<int *>(neigh + (int64_t)j * M);
+    nflat[2 * v] = found;
+    if (found >= 0) nflat[2 * (int64_t)found + 1] = (int)v;
 }
 
 // K6 epilogue: sorted (vertex, entry) pairs -> CSR rows
@@ -453,23 +442,23 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     vert_rep.alloc(M, s);
     out.vkeys.alloc((size_t)M * 8, s);
     int4 *vkeys4 = reinterpret_cast<int4 *>(out.vkeys.p);
+    DevBuf<uint32_t> ka, va, kb, vb;
+    ka.alloc(E, s); va.alloc(E, s);
     assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
-                                             rec_rem.p, rec_rank.p, out.offset.p, vert_rep.p, vkeys4);
+                                             rec_rem.p, rec_rank.p, out.offset.p, vert_rep.p, vkeys4, ka.p, va.p);
     DCRF_LAUNCHED();
     table_to_id_kernel<D><<<ceil_div(M, kThreads), kThreads, 0, s>>>(gd, M, d_tab_start.p, vert_rep.p,
                                                                     slot_of.p, table.p);
     DCRF_LAUNCHED();
 
     out.neigh.alloc((size_t)M * d1, s);
+    DCRF_CUDA(cudaMemsetAsync(out.neigh.p, 0xFF, sizeof(int2) * M * d1, s));
     neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
         M, B, d_vert_start.p, d_tab_start.p, d_tab_mask.p, table.p, vkeys4, out.neigh.p);
     DCRF_LAUNCHED();
 
     // transposed incidence rows: stable sort of entries by vertex id
-    DevBuf<uint32_t> ka, va, kb, vb;
-    ka.alloc(E, s); va.alloc(E, s); kb.alloc(E, s); vb.alloc(E, s);
-    iota_copy_kernel<<<nbe, kThreads, 0, s>>>(out.offset.p, ka.p, va.p, E);
-    DCRF_LAUNCHED();
+    kb.alloc(E, s); vb.alloc(E, s);
     // per-image segments: keys local to an image need fewer radix passes than batch-global ids
     int64_t max_mb = 1;
     std::vector<int64_t> ent_start(B + 1);
