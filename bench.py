@@ -351,9 +351,16 @@ def run_ours(args):
     kernels.sort(key=lambda k: -k["total_ms"])
     top = kernels[0]
     kernel_ms = sum(k["total_ms"] for k in kernels)
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (same batch size only)
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B:
+            traffic = tj["kernels"].get(top["kernel"])
     roofline = {
         "bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-        "frac": top["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "frac": top["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
         "share_of_step": top["total_ms"] / ms_prof,
         "timing": "CUDA events recorded by the library on the launching stream around every launch, in a separate "
                   "pass of the same %d steps run right after the timed region (%.2f ms/step profiled and "

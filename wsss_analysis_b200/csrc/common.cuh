@@ -208,10 +208,6 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
 // value_size<=2 association)
 void launch_slice_plain(const Lattice &lat, const float *val, float *out, int64_t Ntot, int Lp,
                         bool seq, cudaStream_t s);
-// norm[p] <- f(slice value of the all-ones filter) per normalisation type (A.5)
-void launch_norm_finalize(const float *sliced, int Lp, float *norm, int64_t Ntot, int ntype,
-                          cudaStream_t s);
-void launch_fill_ones_col0(float *buf, int64_t Ntot, int Lp, cudaStream_t s);
 // norm[p] = f( K 1 ) for the N pixels of `lat` (A.5), scalar value_size = 1 path
 void launch_kernel_norm(const Lattice &lat, int64_t N, int ntype, float *norm, cudaStream_t s);
 // (L, N_b) row-major blocks  <->  (Ntot, Lp) pixel-major

@@ -682,25 +682,6 @@ __global__ void __launch_bounds__(kThreads) norm_slice_kernel(const int32_t *__r
     norm[p] = res;
 }
 
-// norm[p] from the sliced all-ones filter (column 0 of an Lp-wide buffer)      (A.5)
-__global__ void __launch_bounds__(kThreads) norm_finalize_kernel(const float *__restrict__ sliced,
-                                                                 int Lp, float *__restrict__ norm,
-                                                                 int64_t Ntot, int ntype) {
-    const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (p >= Ntot) return;
-    const float x = sliced[p * Lp];
-    float r;
-    if (ntype == DCRF_NORMALIZE_SYMMETRIC) r = (float)(1.0 / sqrt((double)x + 1e-20));
-    else r = (float)(1.0 / ((double)x + 1e-20));
-    norm[p] = r;
-}
-
-__global__ void __launch_bounds__(kThreads) fill_ones_col0_kernel(float *__restrict__ buf, int64_t n4) {
-    // buf viewed as float4 rows of width Lp = 4: (1, 0, 0, 0)
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n4) st4(buf + i * 4, make_float4(1.f, 0.f, 0.f, 0.f));
-}
-
 // ---------------------------------------------------------------------------------------------
 // layout changes at the API boundary: (L, N_b) row-major blocks <-> (Ntot, Lp) pixel-major
 // ---------------------------------------------------------------------------------------------
@@ -985,13 +966,6 @@ void launch_slice_pairwise_only(const SliceTerm &t, float *out, int64_t Ntot, in
     DCRF_LAUNCHED();
 }
 
-void launch_norm_finalize(const float *sliced, int Lp, float *norm, int64_t Ntot, int ntype,
-                          cudaStream_t s) {
-    if (Ntot == 0) return;
-    norm_finalize_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(sliced, Lp, norm, Ntot, ntype);
-    DCRF_LAUNCHED();
-}
-
 void launch_kernel_norm(const Lattice &lat, int64_t N, int ntype, float *norm, cudaStream_t s) {
     if (N == 0 || lat.M == 0) return;
     DevBuf<float> a, b;
@@ -1009,13 +983,6 @@ void launch_kernel_norm(const Lattice &lat, int64_t N, int ntype, float *norm, c
     const float alpha = 1.0f / (1.0f + powf(2.0f, (float)-lat.d));
     norm_slice_kernel<<<ceil_div(N, kThreads), kThreads, 0, s>>>(lat.offset.p, lat.bary.p, cur, lat.d, alpha, norm,
                                                               N, ntype);
-    DCRF_LAUNCHED();
-}
-
-void launch_fill_ones_col0(float *buf, int64_t Ntot, int Lp, cudaStream_t s) {
-    DCRF_REQUIRE(Lp == 4, DCRF_EINVAL, "fill_ones_col0 expects Lp == 4");
-    if (Ntot == 0) return;
-    fill_ones_col0_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(buf, Ntot);
     DCRF_LAUNCHED();
 }
 
