@@ -161,6 +161,8 @@ struct Lattice {
     DevBuf<int2> ent;              // [E] (vertex id, barycentric weight bits) of entry e
     DevBuf<int2> csr_ent;          // [E] (pixel, weight * pre-norm[pixel] bits) of each sorted entry
     DevBuf<int> row_counter;       // [1] dynamic row-chunk dispenser of the fast splat
+    DevBuf<int32_t> long_rows;     // rows with more than kSplatLongRow entries (tail summed by a whole CTA)
+    DevBuf<int> n_long;            // [1] their number (device side)
 };
 
 void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
@@ -198,6 +200,7 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
 // fast path: packed tables, weights pre-multiplied by the pre-normalisation, FMA accumulation
 void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s);
 void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s);
+void launch_find_long_rows(Lattice &lat, cudaStream_t s);
 // out <- in + 0.5 (in[n1] + in[n2]) along axis j  (A.4 blur)
 void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
                  cudaStream_t s);

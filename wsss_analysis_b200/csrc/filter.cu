@@ -168,6 +168,10 @@ __device__ __forceinline__ void fma4(float4 &acc, float w, const float4 q) {
 // row is still summed by ONE group in ascending entry order, so the result does not depend on the
 // schedule: bit-deterministic run to run.
 constexpr int kSplatChunk = 32;
+// Rows longer than this (flat image regions collapse the bilateral lattice to a few vertices with
+// thousands of entries each) are cut: one lane group sums the first kSplatLongRow entries here, a
+// whole CTA per row sums the tail in splat_long_tail_kernel.  Natural images have no such row.
+constexpr int kSplatLongRow = 256;
 
 template <int G, int SB>
 __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
             if (need) {
                 nv = take ? row : -1;
                 ns = b0;
-                ns1 = b1;
+                ns1 = min(b1, b0 + kSplatLongRow);  // the rest of a very long row: splat_long_tail_kernel
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
@@ -259,6 +263,60 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
 #pragma unroll
         for (int i = 0; i < SB; i++) e_cur[i] = e_next[i];
         if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
+    }
+}
+
+// rows with more than kSplatLongRow entries (found at build time, any order: rows are independent)
+__global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t *__restrict__ csr_start, int64_t M,
+                                                                  int32_t *__restrict__ long_rows,
+                                                                  int *__restrict__ n_long) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= M) return;
+    if (csr_start[v + 1] - csr_start[v] > kSplatLongRow) long_rows[atomicAdd(n_long, 1)] = (int32_t)v;
+}
+
+// val[v] += sum of the entries beyond the first kSplatLongRow of each long row v.  One CTA per row:
+// lane group k sums entries k, k + n_groups, ... in order, then the groups are combined by a fixed
+// binary tree in shared memory => deterministic.
+template <int G>
+__global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
+    const int32_t *__restrict__ csr_start, const int2 *__restrict__ csr_ent, const float4 *__restrict__ Q4,
+    float4 *__restrict__ val4, const int32_t *__restrict__ long_rows, const int *__restrict__ n_long, int g_rt) {
+    extern __shared__ float4 part[];  // [n_groups][g]
+    const int g = G ? G : g_rt;
+    const int n_groups = kThreads / g;
+    const int k = threadIdx.x / g, c = threadIdx.x - k * g;
+    const bool on = k < n_groups;
+    const int n = *n_long;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int v = long_rows[i];
+        const int s0 = csr_start[v] + kSplatLongRow, s1 = csr_start[v + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on)
+            for (int s = s0 + k; s < s1; s += n_groups) {
+                const int2 e = __ldg(csr_ent + s);
+                fma4(acc, __int_as_float(e.y), __ldg(Q4 + ((unsigned)e.x * g + c)));
+            }
+        if (on) part[k * g + c] = acc;
+        __syncthreads();
+        int width = 1;
+        while (width < n_groups) width <<= 1;
+        for (int half = width >> 1; half > 0; half >>= 1) {
+            if (on && k < half && k + half < n_groups) {
+                float4 a = part[k * g + c];
+                const float4 b = part[(k + half) * g + c];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                part[k * g + c] = a;
+            }
+            __syncthreads();
+        }
+        if (on && k == 0) {
+            float4 o = val4[(unsigned)v * g + c];
+            const float4 t = part[c];
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            val4[(unsigned)v * g + c] = o;
+        }
+        __syncthreads();
     }
 }
 
@@ -848,11 +906,22 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
     DCRF_LAUNCHED();
 }
 
+void launch_find_long_rows(Lattice &lat, cudaStream_t s) {
+    lat.long_rows.alloc((size_t)(lat.E / kSplatLongRow + 1), s);
+    lat.n_long.alloc(1, s);
+    DCRF_CUDA(cudaMemsetAsync(lat.n_long.p, 0, sizeof(int), s));
+    if (lat.M == 0) return;
+    find_long_rows_kernel<<<ceil_div(lat.M, kThreads), kThreads, 0, s>>>(lat.csr_start.p, lat.M, lat.long_rows.p,
+                                                                      lat.n_long.p);
+    DCRF_LAUNCHED();
+}
+
 void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s) {
     if (lat.E == 0) return;
     lat.ent.alloc(lat.E, s);
     lat.csr_ent.alloc(lat.E, s);
     lat.row_counter.alloc(1, s);
+    launch_find_long_rows(lat, s);
     pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
         lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, lat.ent.p, lat.csr_ent.p, lat.E);
     DCRF_LAUNCHED();
@@ -890,8 +959,13 @@ void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, c
                                                                      reinterpret_cast<float4 *>(val), (int)lat.M,
                                                                      g, lat.row_counter.p);
         }
+        // tail of very long rows (no-op grid when the lattice has none; the count lives on the device)
+        splat_long_tail_kernel<G><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(
+            lat.csr_start.p, lat.csr_ent.p, reinterpret_cast<const float4 *>(Q), reinterpret_cast<float4 *>(val),
+            lat.long_rows.p, lat.n_long.p, g);
     });
     DCRF_LAUNCHED();
+    g_launches.fetch_add(1);
 }
 
 void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
