@@ -109,6 +109,21 @@ int dcrf_synchronize(dcrf_t *h);
 /* Replaces `d.setUnaryEnergy(U)` (03c_hsn/utilities.py:432).  U: concatenated (L, N_b) blocks. */
 int dcrf_set_unary(dcrf_t *h, const float *U, int on_device);
 
+/* Unary construction on the GPU, replacing the NumPy glue in front of setUnaryEnergy:
+ *  - from class probabilities: `unary_from_softmax(sm, scale, clip)` [EXT pydensecrf.utils] as called
+ *    at 03c_hsn/utilities.py:431.  probs: concatenated (L, N_b) blocks, float64 (is_f64) or float32;
+ *    U = -log(clip(scale*p + (1-scale)/L, clip, 1)) in double, stored as float32.  scale = 1 and
+ *    has_clip = 1, clip = 1e-5 are the defaults the reference uses.
+ *  - from a feature map: SEC/DSRG `crf_inference(..., use_log=True)` ([EXT] lib/crf.py; call sites
+ *    03a_sec-dsrg/SEC.py:275, model.py:689): feat = concatenated (H_b, W_b, L) float32 blocks,
+ *    U = -log softmax_L(feat) (use_log) or -log(feat).
+ *  - from hard labels: `unary_from_labels(labels, L, gt_prob, zero_unsure)` [EXT] as used by
+ *    crf_inference_label (03b_irn/step/cam_to_ir_label.py:35).  labels: concatenated int32. */
+int dcrf_set_unary_from_probs(dcrf_t *h, const void *probs, int is_f64, double scale, double clip,
+                              int has_clip, int on_device);
+int dcrf_set_unary_from_logits(dcrf_t *h, const float *feat, int use_log, int on_device);
+int dcrf_set_unary_from_labels(dcrf_t *h, const int32_t *labels, float gt_prob, int zero_unsure, int on_device);
+
 /* Replaces `d.addPairwiseGaussian(sxy=(sx,sy), compat=...)` (03c_hsn/utilities.py:435).
  * compat: 1 float (Potts), L floats (diagonal) or L*L floats row-major (matrix); HOST memory. */
 int dcrf_add_pairwise_gaussian(dcrf_t *h, float sx, float sy, int compat_kind, const float *compat,

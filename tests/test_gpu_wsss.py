@@ -196,3 +196,49 @@ def test_batch_pipeline_matches_blocking_calls():
         assert len(g_) == len(r_)
         for a, b in zip(g_, r_):
             assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_gpu_unary_construction_matches_numpy():
+    """dcrf_set_unary_from_{probs,logits,labels} against pydensecrf.utils-style NumPy unaries: the
+    unary is read back through inference(0) = softmax(-U)."""
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200 import utils, wsss
+
+    sizes, L = [(37, 23), (16, 40)], 6
+    rng = np.random.default_rng(0)
+
+    def q0(setter):
+        d = G.DenseCRFBatch(sizes, L)
+        setter(d)
+        return d.inference(0)
+
+    def ref_q0(Us):
+        return q0(lambda d: d.setUnaryEnergy(Us))
+
+    probs = [S.blob_probs(L, h, w, seed=i) for i, (w, h) in enumerate(sizes)]
+    probs[0][2, :3, :3] = 0.0  # exercises the clip
+    for kw in ({}, {"scale": 0.6}, {"clip": None, "scale": 0.9}):
+        got = q0(lambda d: d.setUnaryFromSoftmax(probs, **kw))
+        want = ref_q0([utils.unary_from_softmax(p, **kw) for p in probs])
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
+    p32 = [p.astype(np.float32) for p in probs]
+    for a, b in zip(q0(lambda d: d.setUnaryFromSoftmax(p32)), ref_q0([utils.unary_from_softmax(p) for p in p32])):
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
+
+    feats = [rng.standard_normal((h, w, L)).astype(np.float32) * 3 for (w, h) in sizes]
+    for use_log in (True,):
+        got = q0(lambda d: d.setUnaryFromLogits(feats, use_log))
+        want = ref_q0([wsss._unary_from_featmap(f, use_log) for f in feats])
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=5e-6, atol=1e-9)
+
+    labels = [rng.integers(0, L, (h, w)) for (w, h) in sizes]
+    for zu in (False, True):
+        got = q0(lambda d: d.setUnaryFromLabels(labels, 0.7, zero_unsure=zu))
+        want = ref_q0([utils.unary_from_labels(lab, L, 0.7, zero_unsure=zu) for lab in labels])
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
+    with pytest.raises(ValueError, match="label out of range"):
+        q0(lambda d: d.setUnaryFromLabels([lab + L for lab in labels], 0.7, zero_unsure=False))

@@ -27,6 +27,9 @@ SIGNATURES = {
     "dcrf_set_option": (_i, [_vp, _i, _i]),
     "dcrf_synchronize": (_i, [_vp]),
     "dcrf_set_unary": (_i, [_vp, _vp, _i]),
+    "dcrf_set_unary_from_probs": (_i, [_vp, _vp, _i, C.c_double, C.c_double, _i, _i]),
+    "dcrf_set_unary_from_logits": (_i, [_vp, _vp, _i, _i]),
+    "dcrf_set_unary_from_labels": (_i, [_vp, _vp, _f, _i, _i]),
     "dcrf_add_pairwise_gaussian": (_i, [_vp, _f, _f, _i, _vp, _i, _i]),
     "dcrf_add_pairwise_bilateral": (_i, [_vp, _f, _f, _f, _f, _f, _vp, _i, _i, _vp, _i, _i]),
     "dcrf_add_pairwise_energy": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i]),

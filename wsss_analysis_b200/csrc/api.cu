@@ -524,6 +524,68 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
     });
 }
 
+int dcrf_set_unary_from_probs(dcrf_t *h, const void *probs, int is_f64, double scale, double clip,
+                              int has_clip, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && probs, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+        DCRF_REQUIRE(scale > 0.0 && scale <= 1.0, DCRF_EINVAL, "`scale` needs to be in (0,1]");
+        DeviceGuard guard(h->device);
+        const size_t n = (size_t)total_ln(h);
+        const void *src = probs;
+        DevBuf<double> stage64;
+        DevBuf<float> stage32;
+        if (!on_device) {
+            if (is_f64) src = to_device(h, (const double *)probs, n, 0, stage64);
+            else src = to_device(h, (const float *)probs, n, 0, stage32);
+        }
+        launch_unary_from_probs(src, is_f64, h->unary.p, h->geom, h->L, h->Lp, scale, clip, has_clip, h->stream);
+        if (!on_device) host_sync(h);
+        h->unary_set = true;
+        h->q_valid = false;
+    });
+}
+
+int dcrf_set_unary_from_logits(dcrf_t *h, const float *feat, int use_log, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && feat, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+        DeviceGuard guard(h->device);
+        DevBuf<float> stage;
+        const float *src = to_device(h, feat, (size_t)total_ln(h), on_device, stage);
+        launch_unary_from_logits(src, h->unary.p, h->geom.Ntot, h->L, h->Lp, use_log, h->stream);
+        if (!on_device) host_sync(h);
+        h->unary_set = true;
+        h->q_valid = false;
+    });
+}
+
+int dcrf_set_unary_from_labels(dcrf_t *h, const int32_t *labels, float gt_prob, int zero_unsure, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && labels, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L >= 2, DCRF_ESTATE, "unary_from_labels needs at least 2 labels");
+        DCRF_REQUIRE(gt_prob > 0.f && gt_prob < 1.f, DCRF_EINVAL, "`gt_prob must be in (0,1).");
+        DeviceGuard guard(h->device);
+        DevBuf<int32_t> stage;
+        DevBuf<int> bad;
+        const int32_t *src = to_device(h, labels, (size_t)h->geom.Ntot, on_device, stage);
+        bad.alloc(1, h->stream);
+        DCRF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), h->stream));
+        // energies in double like NumPy, stored as float32
+        const float n_energy = (float)(-log((1.0 - (double)gt_prob) / (double)(h->L - 1)));
+        const float p_energy = (float)(-log((double)gt_prob));
+        const float unsure = (float)(-log(1.0 / (double)h->L));
+        launch_unary_from_labels(src, h->unary.p, h->geom.Ntot, h->L, h->Lp, n_energy, p_energy, unsure,
+                                 zero_unsure, bad.p, h->stream);
+        int h_bad = 0;
+        DCRF_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        DCRF_CUDA(cudaStreamSynchronize(h->stream));
+        DCRF_REQUIRE(h_bad == 0, DCRF_EINVAL, "label out of range in unary_from_labels");
+        h->unary_set = true;
+        h->q_valid = false;
+    });
+}
+
 int dcrf_add_pairwise_gaussian(dcrf_t *h, float sx, float sy, int compat_kind, const float *compat,
                                int kernel_type, int normalization_type) {
     return guarded([&] {

@@ -216,6 +216,13 @@ void launch_kernel_norm(const Lattice &lat, int64_t N, int ntype, float *norm, c
 // (L, N_b) row-major blocks  <->  (Ntot, Lp) pixel-major
 void launch_ln_to_pm(const float *ln, float *pm, const BatchGeom &g, int L, int Lp, cudaStream_t s);
 void launch_pm_to_ln(const float *pm, float *ln, const BatchGeom &g, int L, int Lp, cudaStream_t s);
+// unary construction on the GPU (wrappers' NumPy glue): straight into the pixel-major unary buffer
+void launch_unary_from_probs(const void *probs, int is_f64, float *pm, const BatchGeom &g, int L, int Lp,
+                             double scale, double clip_lo, int has_clip, cudaStream_t s);
+void launch_unary_from_logits(const float *feat, float *pm, int64_t Ntot, int L, int Lp, int use_log,
+                              cudaStream_t s);
+void launch_unary_from_labels(const int32_t *labels, float *pm, int64_t Ntot, int L, int Lp, float n_energy,
+                              float p_energy, float unsure_energy, int zero_unsure, int *bad, cudaStream_t s);
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s);
 // deterministic double-precision KL terms
 void launch_kl(const float *Q, const float *unary, const float *const *pair_out, int n_pair,

@@ -810,6 +810,121 @@ __global__ void __launch_bounds__(kThreads) pm_to_ln_kernel(const float *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Unary construction on the GPU (the NumPy glue of the reference's wrappers):
+// results go straight into the pixel-major (Ntot, Lp) unary buffer.
+// ---------------------------------------------------------------------------------------------
+// unary_from_softmax (pydensecrf.utils [EXT], called at 03c_hsn/utilities.py:431):
+//   U = -log(clip(scale * p + (1 - scale) / L, clip, 1)) computed in double like NumPy, stored as f32.
+// probs: concatenated (L, N_b) blocks, float64 or float32.  grid (ceil(maxN/128), B).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) unary_from_probs_kernel(const T *__restrict__ probs,
+                                                                    float *__restrict__ pm,
+                                                                    const int *__restrict__ pix_start, int L, int Lp,
+                                                                    double scale, double clip_lo, int has_clip) {
+    extern __shared__ float tile[];
+    const int b = blockIdx.y;
+    const int64_t ps = pix_start[b];
+    const int Nb = (int)(pix_start[b + 1] - ps);
+    const int p0 = blockIdx.x * kTP;
+    if (p0 >= Nb) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T *src = probs + ps * L + p0;
+    const int np = min(kTP, Nb - p0);
+    const double uni = (1.0 - scale) / (double)L;
+    for (int l = warp; l < Lp; l += kWarps) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int pp = lane + 32 * k;
+            float u = 0.f;
+            if (l < L && pp < np) {
+                double v = (double)src[(int64_t)l * Nb + pp];
+                if (scale != 1.0) v = scale * v + uni;
+                if (has_clip) v = fmin(fmax(v, clip_lo), 1.0);
+                u = (float)(-log(v));
+            }
+            tile[l * (kTP + 1) + pp] = u;
+        }
+    }
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(pm + (ps + p0) * Lp);
+    const int g = Lp >> 2;
+    for (int i = threadIdx.x; i < np * g; i += kThreads) {
+        const int pp = i / g, l = (i - pp * g) * 4;
+        dst[i] = make_float4(tile[l * (kTP + 1) + pp], tile[(l + 1) * (kTP + 1) + pp],
+                             tile[(l + 2) * (kTP + 1) + pp], tile[(l + 3) * (kTP + 1) + pp]);
+    }
+}
+
+// crf_inference(use_log = True) of SEC/DSRG ([EXT] lib/crf.py; call sites SEC.py:275, model.py:689):
+//   p = softmax over the channel axis of an (H, W, C) feature map, U = -log p  (float32 math).
+// feat: concatenated (N_b, C) blocks = already pixel-major.  One lane group per pixel.
+template <int G>
+__global__ void __launch_bounds__(kThreads) unary_from_logits_kernel(const float *__restrict__ feat,
+                                                                     float *__restrict__ pm, int64_t Ntot, int L,
+                                                                     int g_rt, int use_log) {
+    const RowMap<G> rm(g_rt);
+    const int g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < Ntot;
+    const int64_t p = act ? p64 : 0;
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int l = c * 4 + i;
+        f[i] = l < L ? feat[p * L + l] : -INFINITY;
+    }
+    const int lane = threadIdx.x & 31, gbase = lane - c;
+    float u[4];
+    if (use_log) {
+        float m = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), mx = -INFINITY;
+        for (int i = 0; i < g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
+        float e[4], ls = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { e[i] = expf(f[i] - mx); ls += e[i]; }
+        float sum = 0.f;
+        for (int i = 0; i < g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = -logf(e[i] / sum);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = -logf(f[i]);
+    }
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (c * 4 + i >= L) u[i] = 0.f;
+        st4(pm + (p * g + c) * 4, make_float4(u[0], u[1], u[2], u[3]));
+    }
+}
+
+// unary_from_labels (pydensecrf.utils [EXT]; used by crf_inference_label, cam_to_ir_label.py:35)
+__global__ void __launch_bounds__(kThreads) unary_from_labels_kernel(const int32_t *__restrict__ labels,
+                                                                     float *__restrict__ pm, int64_t Ntot, int L,
+                                                                     int Lp, float n_energy, float p_energy,
+                                                                     float unsure_energy, int zero_unsure,
+                                                                     int *__restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= Ntot * Lp) return;
+    const int64_t p = i / Lp;
+    const int l = (int)(i - p * Lp);
+    const int lab = labels[p];
+    float u = 0.f;
+    if (l < L) {
+        if (zero_unsure) {
+            // classes are 1-based, 0 = unsure (uniform); NumPy's U[labels - 1] wraps label 0 to L - 1
+            // before the unsure columns are overwritten, so only the final state matters
+            if (lab == 0) u = unsure_energy;
+            else u = (l == lab - 1) ? p_energy : n_energy;
+            if (lab < 0 || lab > L) atomicExch(bad, 1);
+        } else {
+            u = (l == lab) ? p_energy : n_energy;
+            if (lab < 0 || lab >= L) atomicExch(bad, 1);
+        }
+    }
+    pm[i] = u;
+}
+
 // first maximum wins, like np.argmax
 __global__ void __launch_bounds__(kThreads) argmax_kernel(const float *__restrict__ pm,
                                                           int32_t *__restrict__ labels, int64_t Ntot,
@@ -1102,6 +1217,44 @@ void launch_kl(const float *Q, const float *unary, const float *const *pair_out,
                                                     partial.p);
     DCRF_LAUNCHED();
     kl_final_kernel<<<1, 256, 0, s>>>(partial.p, out);
+    DCRF_LAUNCHED();
+}
+
+void launch_unary_from_probs(const void *probs, int is_f64, float *pm, const BatchGeom &g, int L, int Lp,
+                             double scale, double clip_lo, int has_clip, cudaStream_t s) {
+    if (g.Ntot == 0) return;
+    dim3 grid(ceil_div(max_image_pixels(g), kTP), g.B);
+    const size_t smem = sizeof(float) * Lp * (kTP + 1);
+    if (is_f64) {
+        if (smem > 48 * 1024)
+            DCRF_CUDA(cudaFuncSetAttribute(unary_from_probs_kernel<double>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unary_from_probs_kernel<double><<<grid, kThreads, smem, s>>>((const double *)probs, pm, g.d_pix_start, L, Lp,
+                                                                    scale, clip_lo, has_clip);
+    } else {
+        if (smem > 48 * 1024)
+            DCRF_CUDA(cudaFuncSetAttribute(unary_from_probs_kernel<float>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unary_from_probs_kernel<float><<<grid, kThreads, smem, s>>>((const float *)probs, pm, g.d_pix_start, L, Lp,
+                                                                   scale, clip_lo, has_clip);
+    }
+    DCRF_LAUNCHED();
+}
+
+void launch_unary_from_logits(const float *feat, float *pm, int64_t Ntot, int L, int Lp, int use_log,
+                              cudaStream_t s) {
+    if (Ntot == 0) return;
+    const int g = Lp / 4;
+    const int nb = ceil_div(Ntot, rows_per_block(g));
+    DCRF_DISPATCH_G(g, { unary_from_logits_kernel<G><<<nb, kThreads, 0, s>>>(feat, pm, Ntot, L, g, use_log); });
+    DCRF_LAUNCHED();
+}
+
+void launch_unary_from_labels(const int32_t *labels, float *pm, int64_t Ntot, int L, int Lp, float n_energy,
+                              float p_energy, float unsure_energy, int zero_unsure, int *bad, cudaStream_t s) {
+    if (Ntot == 0) return;
+    unary_from_labels_kernel<<<ceil_div(Ntot * Lp, kThreads), kThreads, 0, s>>>(
+        labels, pm, Ntot, L, Lp, n_energy, p_energy, unsure_energy, zero_unsure, bad);
     DCRF_LAUNCHED();
 }
 

@@ -376,6 +376,37 @@ class DenseCRFBatch(_Model):
     def addPairwiseEnergy(self, *a, **k):
         raise NotImplementedError("addPairwiseEnergy is single-image only")
 
+    # -- unary construction on the GPU (the NumPy glue of the reference's wrappers) --
+    def setUnaryFromSoftmax(self, probs, scale=None, clip=1e-5):
+        """`setUnaryEnergy(unary_from_softmax(probs, scale, clip))` without the host-side log:
+        probs = per-image (L, ...) class probabilities (list, or one concatenated array), float64
+        or float32 (03c_hsn/utilities.py:431-432)."""
+        if isinstance(probs, (list, tuple)):
+            dt = np.float64 if np.asarray(probs[0]).dtype == np.float64 else np.float32
+        else:
+            dt = np.float64 if probs.dtype == np.float64 else np.float32
+        x = self._flat(probs, dt, self._npix * self._L, "probs")
+        a = np.ascontiguousarray(x, dtype=dt).reshape(-1)
+        if scale is not None and not 0 < scale <= 1:
+            raise AssertionError("`scale` needs to be in (0,1]")
+        _lib.check(self._lib.dcrf_set_unary_from_probs(
+            self._h, a.ctypes.data, 1 if dt == np.float64 else 0, 1.0 if scale is None else float(scale),
+            0.0 if clip is None else float(clip), 0 if clip is None else 1, 0))
+
+    def setUnaryFromLogits(self, feats, use_log=True):
+        """Unary of SEC/DSRG's crf_inference: feats = per-image (H, W, L) float32 feature maps;
+        U = -log softmax_L(feat) (use_log) or -log(feat)."""
+        x = self._flat(feats, np.float32, self._npix * self._L, "feats")
+        a = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        _lib.check(self._lib.dcrf_set_unary_from_logits(self._h, a.ctypes.data, 1 if use_log else 0, 0))
+
+    def setUnaryFromLabels(self, labels, gt_prob, zero_unsure=True):
+        """`setUnaryEnergy(unary_from_labels(labels, L, gt_prob, zero_unsure))` on the GPU."""
+        x = self._flat(labels, np.int32, self._npix, "labels")
+        a = np.ascontiguousarray(x, dtype=np.int32).reshape(-1)
+        _lib.check(self._lib.dcrf_set_unary_from_labels(self._h, a.ctypes.data, float(gt_prob),
+                                                        1 if zero_unsure else 0, 0))
+
     def addPairwiseGaussian(self, sxy, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
         sx, sy = _pair(sxy, 2, "sxy")
         kind, c = _compat(compat, self._L)

@@ -17,7 +17,7 @@ unary construction the reference also does in NumPy; the CRF itself has no CPU p
 import numpy as np
 
 from .densecrf import DenseCRFBatch
-from .utils import unary_from_labels, unary_from_softmax
+from .utils import unary_from_labels, unary_from_softmax  # noqa: F401  (host forms, kept for callers)
 
 __all__ = ["dcrf_process", "crf_inference", "crf_inference_batch", "sec_crf_layer", "crf_inference_label",
            "crf_inference_label_batch", "IRN_CRF_CONFIG"]
@@ -59,7 +59,7 @@ def dcrf_process(probs, images, config, device=None):
         if n_act == 0:
             continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0
         d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
-        d.setUnaryEnergy([np.ascontiguousarray(unary_from_softmax(probs[i, active[i]])) for i in idx])
+        d.setUnaryFromSoftmax([probs[i, active[i]] for i in idx])  # clip + -log on the GPU (utilities.py:431)
         d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
         d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=[np.uint8(images[i]) for i in idx],
                                compat=bilat_compat)
@@ -91,7 +91,7 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
     Returns a list of (H_b, W_b, C) float32 marginals."""
     sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     d = DenseCRFBatch(sizes, num_classes, device=device)
-    d.setUnaryEnergy([_unary_from_featmap(f, use_log) for f in featmaps])
+    d.setUnaryFromLogits([np.asarray(f, dtype=np.float32) for f in featmaps], use_log)
     d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
     d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
                            rgbim=[np.ascontiguousarray(im, dtype=np.uint8) for im in imgs],
@@ -131,8 +131,7 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
     cfg = dict(IRN_CRF_CONFIG if crf_config is None else crf_config)
     sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     d = DenseCRFBatch(sizes, n_labels, device=device)
-    d.setUnaryEnergy([unary_from_labels(np.asarray(lab), n_labels, gt_prob=gt_prob, zero_unsure=False)
-                      for lab in labels])
+    d.setUnaryFromLabels([np.asarray(lab) for lab in labels], gt_prob=gt_prob, zero_unsure=False)
     d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
     # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
     d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
