@@ -71,6 +71,10 @@ int64_t dcrf_launch_count(void);
  * depending on PyTorch for stream objects.  The library keeps one device-memory pool per stream;
  * dcrf_stream_destroy also releases that pool. */
 int dcrf_stream_create(int device, void **stream_out);
+/* The per-stream pools keep freed device memory cached for the next image (release threshold =
+ * max).  dcrf_trim_memory() synchronises the current device and returns all cached, unused memory
+ * of every pool to the driver. */
+int dcrf_trim_memory(void);
 int dcrf_stream_destroy(void *stream);
 
 /* Replaces `dcrf.DenseCRF2D(w, h, nlabels)` (03c_hsn/utilities.py:427; width first).

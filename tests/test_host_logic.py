@@ -120,3 +120,11 @@ def test_bench_algorithmic_bytes_formula():
     survey = 12 * L * N + sum(16 * (d + 1) * N + 8 * L * M + (d + 1) * (8 * L * M + 8 * M) for d, M in ((2, Mg), (5, Mb)))
     extra = 4 * L * N + 4 * 4 * N + 4 * (Mg + Mb)
     assert per_iter == survey + extra
+
+
+def test_wrapper_batches_are_chunked_below_the_int32_entry_limit(monkeypatch):
+    assert wsss._MAX_BATCH_PIXELS * 6 < 2 ** 31
+    monkeypatch.setattr(wsss, "_MAX_BATCH_PIXELS", 25)
+    assert wsss._chunks(range(5), [10] * 5) == [[0, 1], [2, 3], [4]]
+    assert wsss._chunks([0, 2, 4], [30, 1, 2, 3, 40]) == [[0], [2], [4]]  # an over-size image runs alone
+    assert wsss._chunks([], []) == []

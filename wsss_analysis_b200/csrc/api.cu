@@ -84,6 +84,11 @@ cudaMemPool_t stream_pool(cudaStream_t stream) {
     return pool;
 }
 
+static void trim_all_pools() {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto &kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
+}
+
 void stream_pool_release(cudaStream_t stream) {
     std::lock_guard<std::mutex> lock(g_pool_mu);
     auto it = g_pools.find(stream);
@@ -467,6 +472,13 @@ void dcrf_destroy(dcrf_t *h) {
     } catch (...) {
     }
     delete h;
+}
+
+int dcrf_trim_memory(void) {
+    return guarded([&] {
+        DCRF_CUDA(cudaDeviceSynchronize());
+        trim_all_pools();
+    });
 }
 
 int dcrf_stream_create(int device, void **stream_out) {

@@ -488,6 +488,11 @@ class DenseCRFBatch(_Model):
     stepInference = klDivergence = startInference
 
 
+def trim_memory():
+    """Return the device memory cached by the library's per-stream pools to the driver."""
+    _lib.check(_lib.load().dcrf_trim_memory())
+
+
 def launch_count():
     """Kernels launched by libdcrf_b200.so in this process (bench.py reports it as gpu_launches)."""
     return int(_lib.load().dcrf_launch_count())

@@ -31,6 +31,24 @@ def _active_classes(probs_img):
     return np.where(np.sum(np.sum(probs_img, axis=1), axis=1) > 0)[0]
 
 
+# a handle indexes lattice entries with int32: N * (d + 1) < 2^31 with d = 5; stay well below
+_MAX_BATCH_PIXELS = (1 << 31) // 6 // 2
+
+
+def _chunks(indices, npix):
+    """Split `indices` into consecutive runs whose total pixel count fits one handle."""
+    out, cur, tot = [], [], 0
+    for i in indices:
+        if cur and tot + npix[i] > _MAX_BATCH_PIXELS:
+            out.append(cur)
+            cur, tot = [], 0
+        cur.append(i)
+        tot += npix[i]
+    if cur:
+        out.append(cur)
+    return out
+
+
 def _group_by(keys):
     """indices grouped by key, groups in order of first appearance, indices ascending."""
     groups = {}
@@ -55,7 +73,10 @@ def dcrf_process(probs, images, config, device=None):
     H, W = int(size[0]), int(size[1])
     crf = np.zeros((num_input_images, num_classes, H, W))
     active = [_active_classes(probs[i]) for i in range(num_input_images)]
-    for n_act, idx in _group_by([len(a) for a in active]).items():
+    groups = []
+    for n_act, members in _group_by([len(a) for a in active]).items():
+        groups += [(n_act, c) for c in _chunks(members, [H * W] * num_input_images)]
+    for n_act, idx in groups:
         if n_act == 0:
             continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0
         d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
@@ -89,16 +110,21 @@ def _unary_from_featmap(feat, use_log):
 def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, device=None):
     """Batched `crf_inference`: imgs list of (H_b, W_b, 3) uint8, featmaps list of (H_b, W_b, C).
     Returns a list of (H_b, W_b, C) float32 marginals."""
-    sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
-    d = DenseCRFBatch(sizes, num_classes, device=device)
-    d.setUnaryFromLogits([np.asarray(f, dtype=np.float32) for f in featmaps], use_log)
-    d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
-    d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
-                           rgbim=[np.ascontiguousarray(im, dtype=np.uint8) for im in imgs],
-                           compat=crf_config["bi_compat"])
-    Q = d.inference(crf_config["iterations"])
-    d.close()
-    return [np.transpose(q.reshape((num_classes, h, w)), (1, 2, 0)) for q, (w, h) in zip(Q, sizes)]
+    all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
+    out = [None] * len(imgs)
+    for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
+        sizes = [all_sizes[i] for i in idx]
+        d = DenseCRFBatch(sizes, num_classes, device=device)
+        d.setUnaryFromLogits([np.asarray(featmaps[i], dtype=np.float32) for i in idx], use_log)
+        d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
+        d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
+                               rgbim=[np.ascontiguousarray(imgs[i], dtype=np.uint8) for i in idx],
+                               compat=crf_config["bi_compat"])
+        Q = d.inference(crf_config["iterations"])
+        d.close()
+        for i, q, (w, h) in zip(idx, Q, sizes):
+            out[i] = np.transpose(q.reshape((num_classes, h, w)), (1, 2, 0))
+    return out
 
 
 def crf_inference(img, crf_config, num_classes, featmap, use_log=True, device=None):
@@ -129,17 +155,21 @@ def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, devic
 def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None):
     """Batched `crf_inference_label`: returns a list of (H_b, W_b) int label maps."""
     cfg = dict(IRN_CRF_CONFIG if crf_config is None else crf_config)
-    sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
-    d = DenseCRFBatch(sizes, n_labels, device=device)
-    d.setUnaryFromLabels([np.asarray(lab) for lab in labels], gt_prob=gt_prob, zero_unsure=False)
-    d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
-    # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
-    d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
-                           rgbim=[np.ascontiguousarray(np.asarray(im).astype(np.uint8)) for im in imgs],
-                           compat=cfg["bi_compat"])
-    out = d.map(t)
-    d.close()
-    return [o.astype(np.int64) for o in out]
+    all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
+    out = [None] * len(imgs)
+    for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
+        d = DenseCRFBatch([all_sizes[i] for i in idx], n_labels, device=device)
+        d.setUnaryFromLabels([np.asarray(labels[i]) for i in idx], gt_prob=gt_prob, zero_unsure=False)
+        d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
+        # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
+        d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
+                               rgbim=[np.ascontiguousarray(np.asarray(imgs[i]).astype(np.uint8)) for i in idx],
+                               compat=cfg["bi_compat"])
+        res = d.map(t)
+        d.close()
+        for i, o in zip(idx, res):
+            out[i] = o.astype(np.int64)
+    return out
 
 
 def crf_inference_label(img, labels, dataset=None, t=10, n_labels=21, gt_prob=0.7, device=None):
