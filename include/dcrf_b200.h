@@ -205,6 +205,17 @@ int dcrf_profile_read(dcrf_t *h, int kernel_class, int tag, double *total_ms, in
 int dcrf_confusion_accumulate(const int32_t *gt, const int32_t *pred, int64_t n, int n_classes,
                               int64_t *conf, int64_t *n_bad_pred, int device, void *stream);
 
+/* ---- resizes either side of the path (device pointers) ---------------------------------------- */
+
+/* cv2.resize(labels, (dw, dh), interpolation=cv2.INTER_NEAREST) on an int32 label map:
+ * 03b_irn/step/eval_sem_seg.py:36, 03c_hsn/demo.py:181-183.  Bit-exact index arithmetic. */
+int dcrf_resize_nearest_i32(const int32_t *src, int sh, int sw, int32_t *dst, int dh, int dw, int device,
+                            void *stream);
+/* cv2.resize(featmap, (dw, dh)) (INTER_LINEAR) on a float32 (sh, sw, channels) map:
+ * 03a_sec-dsrg/model.py:686-687,696. */
+int dcrf_resize_bilinear_f32(const float *src, int sh, int sw, int channels, float *dst, int dh, int dw,
+                             int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,8 @@ SIGNATURES = {
     "dcrf_lattice_filter": (_i, [_vp, _i, _vp, _vp, _i]),
     "dcrf_profile_enable": (_i, [_vp, _i]),
     "dcrf_profile_read": (_i, [_vp, _i, _i, C.POINTER(C.c_double), C.POINTER(_i64), _i]),
+    "dcrf_resize_nearest_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp]),
+    "dcrf_resize_bilinear_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "dcrf_confusion_accumulate": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
 }
 

@@ -76,6 +76,42 @@ class ConfusionAccumulator(object):
         return int(self.bad.item())
 
 
+def resize_nearest(labels, size_wh, device=None):
+    """`cv2.resize(labels, (W, H), interpolation=cv2.INTER_NEAREST)` on the GPU
+    (/root/reference/03b_irn/step/eval_sem_seg.py:36, 03c_hsn/demo.py:181-183).  labels: (h, w) integer
+    map (numpy or torch); returns an int32 torch tensor (H, W) on the GPU."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    if not isinstance(labels, torch.Tensor):
+        labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32))
+    src = labels.to(dev, torch.int32).contiguous()
+    W, H = int(size_wh[0]), int(size_wh[1])
+    dst = torch.empty((H, W), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().dcrf_resize_nearest_i32(src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), H, W,
+                                                    dev.index, torch.cuda.current_stream(dev).cuda_stream))
+    return dst
+
+
+def resize_bilinear(featmap, size_wh, device=None):
+    """`cv2.resize(featmap, (W, H))` (INTER_LINEAR) of a float32 (h, w, C) map on the GPU
+    (/root/reference/03a_sec-dsrg/model.py:686-687).  Returns a float32 torch tensor (H, W, C)."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    if not isinstance(featmap, torch.Tensor):
+        featmap = torch.from_numpy(np.ascontiguousarray(featmap, dtype=np.float32))
+    src = featmap.to(dev, torch.float32).contiguous()
+    if src.dim() == 2:
+        src = src.unsqueeze(-1)
+    W, H = int(size_wh[0]), int(size_wh[1])
+    dst = torch.empty((H, W, src.shape[2]), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().dcrf_resize_bilinear_f32(src.data_ptr(), src.shape[0], src.shape[1], src.shape[2],
+                                                     dst.data_ptr(), H, W, dev.index,
+                                                     torch.cuda.current_stream(dev).cuda_stream))
+    return dst
+
+
 def all_reduce_confusion_host(conf, group=None):
     """Host-side (gloo) form of the same collective for CPU-only tests of the sharding logic."""
     import torch
