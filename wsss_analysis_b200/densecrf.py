@@ -115,8 +115,14 @@ class _Model(object):
             torch.cuda.current_stream().synchronize()
 
     def set_async_host(self, on=True):
-        """Host-buffer calls only enqueue their copies; call synchronize() before touching the buffers."""
+        """Calls only enqueue their copies / kernels on the handle's stream; call synchronize() before
+        touching the caller's buffers (host arrays or device tensors) again."""
         _lib.check(self._lib.dcrf_set_option(self._h, 2, 1 if on else 0))
+        self._async = bool(on)
+
+    def _sync_unless_async(self):
+        if not getattr(self, "_async", False):
+            self.synchronize()
 
     def set_exact_arithmetic(self, on=True):
         """Use the specification's float association literally in the iteration kernels (slower)."""
@@ -141,7 +147,7 @@ class _Model(object):
         self._pre_device_input(dev)
         _lib.check(self._lib.dcrf_set_unary(self._h, ptr, dev))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
     def _add_energy(self, features, compat, kernel, normalization):
@@ -154,7 +160,7 @@ class _Model(object):
         _lib.check(self._lib.dcrf_add_pairwise_energy(self._h, ptr, shape[0], dev, kind, c.ctypes.data,
                                                       int(kernel), int(normalization)))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
     def addPairwiseEnergy(self, features, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
@@ -182,7 +188,7 @@ class _Model(object):
         ptr, dev, _, _ = _buffer(out, np.float32, "out")
         assert dev == 1 and tuple(out.shape) == (self._L, self._Ntot)
         _lib.check(self._lib.dcrf_inference(self._h, int(niter), ptr, 1))
-        self.synchronize()
+        self._sync_unless_async()
         return out
 
     def map(self, niter):
@@ -197,7 +203,7 @@ class _Model(object):
         if out is None:
             out = torch.empty((self._Ntot,), dtype=torch.int32, device="cuda:%d" % self._dev_index())
         _lib.check(self._lib.dcrf_map(self._h, int(niter), out.data_ptr(), 1))
-        self.synchronize()
+        self._sync_unless_async()
         return out
 
     def _dev_index(self):
@@ -221,7 +227,7 @@ class _Model(object):
         _lib.check(self._lib.dcrf_step_inference(self._h))
         _lib.check(self._lib.dcrf_get_q(self._h, ptr, dev))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
     def klDivergence(self, Q):
@@ -324,7 +330,7 @@ class DenseCRF2D(_Model):
         _lib.check(self._lib.dcrf_add_pairwise_bilateral(self._h, sx, sy, sr, sg, sb, ptr, dev, kind,
                                                          c.ctypes.data, int(kernel), int(normalization)))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
 
@@ -370,7 +376,7 @@ class DenseCRFBatch(_Model):
         self._pre_device_input(dev)
         _lib.check(self._lib.dcrf_set_unary(self._h, ptr, dev))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
     def addPairwiseEnergy(self, *a, **k):
@@ -424,7 +430,7 @@ class DenseCRFBatch(_Model):
         _lib.check(self._lib.dcrf_add_pairwise_bilateral(self._h, sx, sy, sr, sg, sb, ptr, dev, kind,
                                                          c.ctypes.data, int(kernel), int(normalization)))
         if dev:
-            self.synchronize()
+            self._sync_unless_async()
         del keep
 
     def _split(self, flat, per_elem, shape_fn):
@@ -450,7 +456,7 @@ class DenseCRFBatch(_Model):
         if out is None:
             out = torch.empty((self._Ntot * self._L,), dtype=torch.float32, device="cuda:%d" % self._dev_index())
         _lib.check(self._lib.dcrf_inference(self._h, int(niter), out.data_ptr(), 1))
-        self.synchronize()
+        self._sync_unless_async()
         return out
 
     def map(self, niter, out=None):

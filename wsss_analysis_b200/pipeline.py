@@ -56,7 +56,10 @@ class BatchPipeline(object):
         crf.setUnaryEnergy(unary)
         crf.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
         crf.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"], rgbim=rgb, compat=cfg["bi_compat"])
-        res = crf.map(cfg["iterations"], out=out) if labels else crf.inference(cfg["iterations"], out=out)
+        if hasattr(out, "data_ptr"):   # torch CUDA tensor: device-resident output (inputs may be too)
+            res = crf.map_device(cfg["iterations"], out=out) if labels else crf.inference_device(cfg["iterations"], out=out)
+        else:
+            res = crf.map(cfg["iterations"], out=out) if labels else crf.inference(cfg["iterations"], out=out)
         self._slots[slot] = (crf, res, ticket)
         return ticket
 
