@@ -17,7 +17,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (wsss_analysis_b200) never does.
  *
- * Build:  gcc -O2 -ffp-contract=off -fno-fast-math -fPIC -shared  (see oracle/Makefile)
+ * Build:  gcc -O3 -ffp-contract=off -fno-fast-math -fPIC -shared  (see oracle/Makefile)
  * Float order is defined: no FMA contraction, SSE2 scalar float math (x86-64 default).
  *
  * Layout conventions (Appendix A.1):
