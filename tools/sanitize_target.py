@@ -1,0 +1,27 @@
+"""Small workload touching every kernel family (uniform + mixed batches, flat image long rows, L<=2,
+generic-G, exact mode, GPU unaries, resize, confusion) for compute-sanitizer runs."""
+import sys, os
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np, torch
+from wsss_analysis_b200 import densecrf as G, synthetic as S, evaluation as E, wsss
+
+def batch(sizes, L, imgs=None, exact=False):
+    imgs = imgs or [S.natural_image(h, w, i) for i, (w, h) in enumerate(sizes)]
+    d = G.DenseCRFBatch(sizes, L)
+    if exact: d.set_exact_arithmetic(True)
+    d.setUnaryEnergy([S.random_unary(L, w * h, i) for i, (w, h) in enumerate(sizes)])
+    d.addPairwiseGaussian(sxy=3, compat=3); d.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs, compat=10)
+    q = d.inference(2); lab = d.map(2); d.close(); return q, lab
+
+batch([(48, 36)] * 3, 21)                                   # uniform: replicated Gaussian lattice
+batch([(48, 36), (30, 50)], 6)                              # mixed sizes
+batch([(64, 64)], 21, [np.full((64, 64, 3), 90, np.uint8)]) # flat: long-row tail kernel
+batch([(40, 30)], 2); batch([(40, 30)], 1); batch([(20, 20)], 37); batch([(40, 30)], 5, exact=True)
+probs = np.stack([S.blob_probs(6, 24, 32, seed=i, n_active=3) for i in range(2)])
+wsss.dcrf_process(probs, np.stack([S.histo_image(24, 32, i) for i in range(2)]), (1.5, 3, 40, 13, 10, 3.0))
+wsss.crf_inference_label(S.natural_image(24, 32, 0).astype(np.float32), S.gt_map(24, 32, 4, 0, ignore=0), "voc12", n_labels=4)
+wsss.sec_crf_layer(np.random.default_rng(0).standard_normal((2, 41, 41, 5)).astype(np.float32), np.stack([S.natural_image(41, 41, i) for i in range(2)]).astype(np.float32),
+                   {"g_sxy": 0.25, "g_compat": 3, "bi_sxy": 80 / 12, "bi_srgb": 13, "bi_compat": 10, "iterations": 2}, 5)
+acc = E.ConfusionAccumulator(6); lab = S.gt_map(40, 40, 6, 0, ignore=255)
+acc.update(lab, E.resize_nearest(S.gt_map(10, 10, 6, 1, ignore=0), (40, 40))); E.resize_bilinear(np.ones((5, 7, 3), np.float32), (20, 11))
+print("sanitize target ok", acc.result().sum())
