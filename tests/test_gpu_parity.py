@@ -287,3 +287,30 @@ def test_uniform_batch_shares_the_gaussian_lattice(mods):
             assert np.array_equal(eo.bary.view(np.uint32), eg["bary"].view(np.uint32))
             np.testing.assert_allclose(eg["norm"], o.norm(k), rtol=2e-6, atol=0)
         assert np.abs(o.inference(5) - Qb[i]).max() <= Q_TOL
+
+
+@pytest.mark.parametrize("terms", ["gauss", "bilat", "gauss+bilat+bilat", "bilat+gauss", "energy3d"])
+def test_other_term_combinations(mods, terms):
+    """Anything but (Gaussian, bilateral) takes the generic fast slice: one term, three terms,
+    reversed order, a 3-D position-only kernel through addPairwiseEnergy."""
+    O, G, S = mods
+    from wsss_analysis_b200 import utils
+
+    W, H, L = 44, 33, 7
+    img = S.natural_image(H, W, 21)
+    U = S.random_unary(L, W * H, 21)
+    o, g = O.DenseCRF2D(W, H, L), G.DenseCRF2D(W, H, L)
+    for m in (o, g):
+        m.setUnaryEnergy(U)
+        for t in terms.split("+"):
+            if t == "gauss":
+                m.addPairwiseGaussian(sxy=2, compat=4)
+            elif t == "bilat":
+                m.addPairwiseBilateral(sxy=30, srgb=11, rgbim=img, compat=7)
+            else:
+                f = utils.create_pairwise_bilateral((5, 5), (20,), img[..., 0], chdim=-1)
+                m.addPairwiseEnergy(np.ascontiguousarray(f), compat=5)
+    assert g.num_pairwise() == len(terms.split("+"))
+    Qo, Qg = o.inference(4), g.inference(4)
+    assert np.abs(Qo - Qg).max() <= Q_TOL
+    assert (Qo.argmax(0) == Qg.argmax(0)).mean() >= AGREE

@@ -633,6 +633,61 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const Slic
     }
 }
 
+// Fast fused slice for any other combination of Potts terms (1..4 terms, any dimensions): same
+// arithmetic as above with run-time loops.
+template <int G>
+__global__ void __launch_bounds__(kThreads) slice_softmax_fast_generic_kernel(const SliceArgs a,
+                                                                              const float4 *__restrict__ unary4,
+                                                                              float4 *__restrict__ Q4, unsigned Ntot,
+                                                                              int L, int g_rt) {
+    const RowMap<G> rm(g_rt);
+    const unsigned g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
+    const unsigned p = act ? (unsigned)p64 : 0u;
+    const float4 u = __ldg(unary4 + (p * g + c));
+    float4 t = make_float4(-u.x, -u.y, -u.z, -u.w);
+    for (int k = 0; k < a.n_terms; k++) {
+        const SliceTerm &tm = a.term[k];
+        const int2 *ep = tm.ent + (size_t)p * (tm.d + 1);
+        const float4 *val4 = reinterpret_cast<const float4 *>(tm.val);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r <= tm.d; r++) {
+            const int2 e = __ldg(ep + r);
+            fma4(acc, __int_as_float(e.y), __ldg(val4 + ((unsigned)e.x * g + c)));
+        }
+        float w = tm.potts_w * tm.alpha;
+        if (tm.norm) w *= __ldg(tm.norm + p);
+        t.x = fmaf(w, acc.x, t.x);
+        t.y = fmaf(w, acc.y, t.y);
+        t.z = fmaf(w, acc.z, t.z);
+        t.w = fmaf(w, acc.w, t.w);
+    }
+    const int l0 = c * 4;
+    const float NEG = -INFINITY;
+    if (l0 + 0 >= L) t.x = NEG;
+    if (l0 + 1 >= L) t.y = NEG;
+    if (l0 + 2 >= L) t.z = NEG;
+    if (l0 + 3 >= L) t.w = NEG;
+    const float m = fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w));
+    const int lane = threadIdx.x & 31;
+    const int gbase = lane - c;
+    float mx = NEG;
+    for (int i = 0; i < (int)g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
+    float4 e;
+    e.x = expf(t.x - mx);
+    e.y = expf(t.y - mx);
+    e.z = expf(t.z - mx);
+    e.w = expf(t.w - mx);
+    const float ls = (e.x + e.y) + (e.z + e.w);
+    float sum = 0.f;
+    for (int i = 0; i < (int)g; i++) sum += __shfl_sync(0xffffffffu, ls, (gbase + i) & 31);
+    if (act) {
+        const float inv = 1.0f / sum;
+        Q4[p * g + c] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
+    }
+}
+
 // Q0 = softmax(-U) (startInference), fast-math variant of slice_softmax_kernel with no terms
 template <int G>
 __global__ void __launch_bounds__(kThreads) softmax_unary_fast_kernel(const float4 *__restrict__ unary4,
@@ -1117,6 +1172,17 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
     if (a.fast && potts2 && Ntot * g < ((int64_t)1 << 31)) {
         DCRF_DISPATCH_G(g, {
             slice_softmax_fast_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(
+                a, reinterpret_cast<const float4 *>(unary), reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
+        });
+        DCRF_LAUNCHED();
+        return;
+    }
+    bool all_potts = a.n_terms >= 1 && !a.seq;
+    for (int k = 0; k < a.n_terms; k++)
+        all_potts = all_potts && a.term[k].compat_kind == DCRF_COMPAT_POTTS && a.term[k].ent != nullptr;
+    if (a.fast && all_potts && Ntot * g < ((int64_t)1 << 31)) {
+        DCRF_DISPATCH_G(g, {
+            slice_softmax_fast_generic_kernel<G><<<nb, kThreads, 0, s>>>(
                 a, reinterpret_cast<const float4 *>(unary), reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
         });
         DCRF_LAUNCHED();
