@@ -127,7 +127,9 @@ typedef struct orc_lattice {
     int16_t *keys;        /* M*d */
 } orc_lattice;
 
-/* feature: N x d, pixel-major (Eigen (d,N) column-major) */
+/* Permutohedral::init [EXT], Appendix A.3 steps 1-9; reached from addPairwiseGaussian / Bilateral
+ * (/root/reference/03c_hsn/utilities.py:435, :439-440).
+ * feature: N x d, pixel-major (Eigen (d,N) column-major) */
 orc_lattice *orc_lattice_create(const float *feature, int N, int d) {
     orc_lattice *lat = (orc_lattice *)calloc(1, sizeof(orc_lattice));
     lat->N = N;
@@ -276,6 +278,8 @@ void orc_lattice_export(const orc_lattice *lat, int16_t *keys, int32_t *offsets,
 }
 
 /*
+ * Permutohedral::compute [EXT] (splat / blur / slice), run twice per iteration inside
+ * `d.inference(n)` (/root/reference/03c_hsn/utilities.py:442).
  * A.4 filter.  in/out: N x value_size pixel-major (may alias).
  * Two association variants exist upstream: a scalar path used when value_size <= 2 (blur through a
  * double 0.5, slice as (w*v)*alpha) and a 4-wide float path used otherwise (blur in float,
@@ -359,6 +363,7 @@ typedef struct orc_crf {
     orc_pairwise *pair;
 } orc_crf;
 
+/* `dcrf.DenseCRF2D(w, h, nlabels)` / `DenseCRF(nvar, nlabels)` (/root/reference/03c_hsn/utilities.py:427) */
 orc_crf *orc_crf_create(int N, int L) {
     orc_crf *c = (orc_crf *)calloc(1, sizeof(orc_crf));
     c->N = N;
@@ -439,7 +444,8 @@ int orc_crf_add_pairwise(orc_crf *c, const float *feature_dN, int d, int compat_
     return r;
 }
 
-/* A.2 features: float32 true division of an integer by a float32 parameter */
+/* `d.addPairwiseGaussian(sxy=..., compat=...)` (/root/reference/03c_hsn/utilities.py:435).
+ * A.2 features: float32 true division of an integer by a float32 parameter */
 int orc_crf_add_gaussian_2d(orc_crf *c, int W, int H, float sx, float sy, int compat_kind,
                             const float *compat, int ktype, int ntype) {
     float *f = (float *)malloc(sizeof(float) * (size_t)(W * H > 0 ? W * H : 1) * 2);
@@ -453,6 +459,7 @@ int orc_crf_add_gaussian_2d(orc_crf *c, int W, int H, float sx, float sy, int co
     return r;
 }
 
+/* `d.addPairwiseBilateral(sxy=..., srgb=..., rgbim=..., compat=...)` (/root/reference/03c_hsn/utilities.py:439-440) */
 int orc_crf_add_bilateral_2d(orc_crf *c, int W, int H, float sx, float sy, float sr, float sg,
                              float sb, const uint8_t *im, int compat_kind, const float *compat,
                              int ktype, int ntype) {
@@ -477,7 +484,9 @@ void orc_crf_norm(const orc_crf *c, int k, float *out) {
     memcpy(out, c->pair[k].norm, sizeof(float) * c->N);
 }
 
-/* A.5 + A.6: out = compat( norm (.) K( norm (.) Q ) ), pixel-major N x L */
+/* DenseKernel::filter + LabelCompatibility::apply [EXT] (A.5 + A.6), once per pairwise term and
+ * iteration of `d.inference(n)` (/root/reference/03c_hsn/utilities.py:442):
+ * out = compat( norm (.) K( norm (.) Q ) ), pixel-major N x L */
 static void orc_pairwise_apply(const orc_crf *c, const orc_pairwise *pw, float *out, const float *Q,
                                int transpose) {
     const int N = c->N, L = c->L;
@@ -560,7 +569,8 @@ static void orc_ln_to_pm(const orc_crf *c, const float *ln, float *pm) {
         for (int l = 0; l < c->L; l++) pm[(size_t)p * c->L + l] = ln[(size_t)l * c->N + p];
 }
 
-/* Q_out: row-major (L, N) -- what np.array(Q) yields (03c_hsn/utilities.py:443) */
+/* `Q = d.inference(n_infer)` (/root/reference/03c_hsn/utilities.py:442), DenseCRF::inference [EXT] A.7.
+ * Q_out: row-major (L, N) -- what np.array(Q) yields (03c_hsn/utilities.py:443) */
 void orc_crf_inference(const orc_crf *c, int n_iter, float *Q_out) {
     const size_t n = (size_t)c->N * c->L;
     float *Q = (float *)malloc(sizeof(float) * (n ? n : 1));
