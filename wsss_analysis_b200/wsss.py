@@ -71,24 +71,28 @@ def dcrf_process(probs, images, config, device=None):
     num_input_images, num_classes = probs.shape[0], probs.shape[1]
     size = images.shape[1:3]
     H, W = int(size[0]), int(size[1])
-    crf = np.zeros((num_input_images, num_classes, H, W))
+    # The reference scatters Q back into a zero (B, C, H, W) float64 array and takes np.argmax over C
+    # (utilities.py:421,443-445).  Marginals of active classes are > 0 and sum to 1, inactive slots
+    # are 0 and active class indices ascend, so that argmax equals active[argmax over the active
+    # classes] (first maximum wins in both): only the int32 label map leaves the GPU.
+    out = np.zeros((num_input_images, H, W), dtype=np.int64)
     active = [_active_classes(probs[i]) for i in range(num_input_images)]
     groups = []
     for n_act, members in _group_by([len(a) for a in active]).items():
         groups += [(n_act, c) for c in _chunks(members, [H * W] * num_input_images)]
     for n_act, idx in groups:
         if n_act == 0:
-            continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0
+            continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0 -> label 0
         d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
         d.setUnaryFromSoftmax([probs[i, active[i]] for i in idx])  # clip + -log on the GPU (utilities.py:431)
         d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
         d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=[np.uint8(images[i]) for i in idx],
                                compat=bilat_compat)
-        Q = d.inference(n_infer)
+        labels = d.map(n_infer)
         d.close()
         for j, i in enumerate(idx):
-            crf[i, active[i]] = Q[j].reshape((n_act, H, W))
-    return np.argmax(crf, axis=1)
+            out[i] = active[i][labels[j]]
+    return out
 
 
 def _unary_from_featmap(feat, use_log):
