@@ -314,3 +314,39 @@ def test_other_term_combinations(mods, terms):
     Qo, Qg = o.inference(4), g.inference(4)
     assert np.abs(Qo - Qg).max() <= Q_TOL
     assert (Qo.argmax(0) == Qg.argmax(0)).mean() >= AGREE
+
+
+def test_c_abi_error_codes_and_messages(mods):
+    """Direct ctypes calls: bad arguments come back as DCRF_EINVAL / DCRF_ESTATE with a message,
+    never as a crash (include/dcrf_b200.h error contract)."""
+    import ctypes as C
+
+    from wsss_analysis_b200 import _lib
+
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.dcrf_create(0, 10, 3, -1, None, C.byref(h)) == _lib.DCRF_EINVAL
+    assert b"width/height" in lib.dcrf_last_error()
+    assert lib.dcrf_create(10, 10, 129, -1, None, C.byref(h)) == _lib.DCRF_EINVAL
+    assert lib.dcrf_create(10, 10, 3, 9999, None, C.byref(h)) == _lib.DCRF_EINVAL
+    assert lib.dcrf_create(10, 10, 3, -1, None, C.byref(h)) == _lib.DCRF_OK
+    potts = np.array([1.0], np.float32)
+    assert lib.dcrf_set_unary(h, None, 0) == _lib.DCRF_EINVAL
+    assert lib.dcrf_add_pairwise_gaussian(h, 3.0, 3.0, 7, potts.ctypes.data, 1, 3) == _lib.DCRF_EINVAL
+    assert lib.dcrf_add_pairwise_gaussian(h, 3.0, 3.0, 0, potts.ctypes.data, 1, 9) == _lib.DCRF_EINVAL
+    assert lib.dcrf_add_pairwise_gaussian(h, 3.0, 3.0, 0, None, 1, 3) == _lib.DCRF_EINVAL
+    assert lib.dcrf_step_inference(h) == _lib.DCRF_ESTATE          # before startInference
+    q = np.zeros((3, 100), np.float32)
+    assert lib.dcrf_get_q(h, q.ctypes.data, 0) == _lib.DCRF_ESTATE
+    assert lib.dcrf_inference(h, -1, q.ctypes.data, 0) == _lib.DCRF_EINVAL
+    assert lib.dcrf_lattice_info(h, 0, None, None, None) == _lib.DCRF_EINVAL  # no pairwise term yet
+    feats = np.zeros((8, 100), np.float32)
+    assert lib.dcrf_add_pairwise_energy(h, feats.ctypes.data, 8, 0, 0, potts.ctypes.data, 1, 3) == _lib.DCRF_EINVAL
+    for _ in range(4):
+        assert lib.dcrf_add_pairwise_gaussian(h, 3.0, 3.0, 0, potts.ctypes.data, 1, 3) == _lib.DCRF_OK
+    assert lib.dcrf_add_pairwise_gaussian(h, 3.0, 3.0, 0, potts.ctypes.data, 1, 3) == _lib.DCRF_EINVAL  # max 4 terms
+    assert lib.dcrf_inference(h, 1, q.ctypes.data, 0) == _lib.DCRF_OK
+    np.testing.assert_allclose(q.sum(0), 1.0, atol=1e-5)
+    lib.dcrf_destroy(h)
+    lib.dcrf_destroy(None)  # no-op
+    assert lib.dcrf_launch_count() > 0
