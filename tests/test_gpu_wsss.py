@@ -243,3 +243,17 @@ def test_gpu_unary_construction_matches_numpy():
             np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-9)
     with pytest.raises(ValueError, match="label out of range"):
         q0(lambda d: d.setUnaryFromLabels([lab + L for lab in labels], 0.7, zero_unsure=False))
+
+
+def test_crf_inference_label_shares_lattices_between_label_sets():
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200 import wsss
+
+    imgs = [S.natural_image(40, 52, i).astype(np.float32) for i in range(3)]
+    fg = [S.gt_map(40, 52, 4, i, ignore=0, border=2) for i in range(3)]
+    bg = [S.gt_map(40, 52, 4, 10 + i, ignore=0, border=2) for i in range(3)]
+    both = wsss.crf_inference_label_batch(imgs, fg, n_labels=4, extra_labels=[bg])
+    sep = [wsss.crf_inference_label_batch(imgs, fg, n_labels=4), wsss.crf_inference_label_batch(imgs, bg, n_labels=4)]
+    for k in range(2):
+        for a, b in zip(both[k], sep[k]):
+            assert np.array_equal(a, b)

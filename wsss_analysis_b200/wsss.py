@@ -156,24 +156,31 @@ def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, devic
     return ret.astype(np.float32)
 
 
-def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None):
-    """Batched `crf_inference_label`: returns a list of (H_b, W_b) int label maps."""
+def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None,
+                              extra_labels=()):
+    """Batched `crf_inference_label`: returns a list of (H_b, W_b) int label maps.
+
+    `extra_labels`: further label sets for the SAME images (each a list like `labels`).  The
+    lattices depend on the image only, so they are built once and every label set just replaces
+    the unary -- the VOC branch of cam_to_ir_label.py runs the CRF twice per image (fg threshold
+    :47, bg threshold :52).  With extra sets the return value is a list of result lists."""
     cfg = dict(IRN_CRF_CONFIG if crf_config is None else crf_config)
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
-    out = [None] * len(imgs)
+    label_sets = [labels] + list(extra_labels)
+    outs = [[None] * len(imgs) for _ in label_sets]
     for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
         d = DenseCRFBatch([all_sizes[i] for i in idx], n_labels, device=device)
-        d.setUnaryFromLabels([np.asarray(labels[i]) for i in idx], gt_prob=gt_prob, zero_unsure=False)
         d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
         # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
         d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
                                rgbim=[np.ascontiguousarray(np.asarray(imgs[i]).astype(np.uint8)) for i in idx],
                                compat=cfg["bi_compat"])
-        res = d.map(t)
+        for k, ls in enumerate(label_sets):
+            d.setUnaryFromLabels([np.asarray(ls[i]) for i in idx], gt_prob=gt_prob, zero_unsure=False)
+            for i, o in zip(idx, d.map(t)):
+                outs[k][i] = o.astype(np.int64)
         d.close()
-        for i, o in zip(idx, res):
-            out[i] = o.astype(np.int64)
-    return out
+    return outs[0] if not extra_labels else outs
 
 
 def crf_inference_label(img, labels, dataset=None, t=10, n_labels=21, gt_prob=0.7, device=None):
