@@ -6,7 +6,7 @@
 //   K1  point kernel : features -> elevate -> nearest remainder-0 point -> rank -> barycentric
 //   K2  hash insert  : open-addressing table of lattice keys, slot value = min entry index
 //   K3  numbering    : first-occurrence flags + exclusive scan  => the reference's vertex ids
-//   K4  assign       : offsets, vertex keys, table slot -> vertex id
+//   K4  assign       : offsets, vertex keys; compact (L2-resident) table of vertex ids
 //   K5  neighbours   : +-1 neighbours along each of the d+1 axes by table lookup
 //   K6  CSR          : stable radix sort of entries by vertex id => rows of the transposed
 //                      incidence matrix in ascending entry order (deterministic splat)
@@ -264,13 +264,13 @@ __global__ void __launch_bounds__(kThreads) first_flag_kernel(
     flag[e] = (table[tab_start[b] + slot_of[e]] == (int32_t)e) ? 1 : 0;
 }
 
-// K4a: offsets for all entries; first occurrences also publish their vertex (rep entry + key)
+// K4a: offsets for all entries; first occurrences also publish their vertex key
 template <int D>
 __global__ void __launch_bounds__(kThreads) assign_kernel(
     GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
     const int32_t *__restrict__ slot_of, const int32_t *__restrict__ scanned,
     const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
-    int32_t *__restrict__ offset, int32_t *__restrict__ vert_rep, int4 *__restrict__ vkeys,
+    int32_t *__restrict__ offset, int4 *__restrict__ vkeys,
     uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals) {
     const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (e >= E) return;
@@ -282,23 +282,23 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     sort_keys[e] = (uint32_t)id;  // (vertex, entry) pairs for the CSR sort (K6)
     sort_vals[e] = (uint32_t)e;
     if (rep == (int32_t)e) {
-        vert_rep[id] = (int32_t)e;
         short key[8];
         entry_key<D>(rec_rem[gp], rec_rank[gp], (int)(e - gp * (D + 1)), key);
         vkeys[id] = pack_key(key);
     }
 }
 
-// K4b: table slot: representative entry -> vertex id (one thread per vertex)
-template <int D>
-__global__ void __launch_bounds__(kThreads) table_to_id_kernel(
-    GeomDev g, int64_t M, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ vert_rep,
-    const int32_t *__restrict__ slot_of, int32_t *__restrict__ table) {
+// K4b: compact table of vertex ids, one insert per vertex (keys are unique: plain CAS claim)
+__global__ void __launch_bounds__(kThreads) compact_insert_kernel(
+    int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
+    const int *__restrict__ tab_mask, const int4 *__restrict__ vkeys, int32_t *table) {
     const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (v >= M) return;
-    const int32_t e = vert_rep[v];
-    const int b = find_image(g.pix_start, g.B, e / (D + 1));
-    table[tab_start[b] + slot_of[e]] = (int32_t)v;
+    const int b = find_image(vert_start, B, v);
+    int32_t *tab = table + tab_start[b];
+    const uint32_t mask = (uint32_t)tab_mask[b];
+    uint32_t h = key_hash(vkeys[v]) & mask;
+    while (atomicCAS(&tab[h], -1, (int32_t)v) != -1) h = (h + 1) & mask;
 }
 
 // vert_start[b] = number of first occurrences before image b's first entry
@@ -438,24 +438,44 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     out.M = M;
 
     out.offset.alloc(E, s);
-    DevBuf<int32_t> vert_rep;
-    vert_rep.alloc(M, s);
     out.vkeys.alloc((size_t)M * 8, s);
     int4 *vkeys4 = reinterpret_cast<int4 *>(out.vkeys.p);
     DevBuf<uint32_t> ka, va, kb, vb;
     ka.alloc(E, s); va.alloc(E, s);
     assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
-                                             rec_rem.p, rec_rank.p, out.offset.p, vert_rep.p, vkeys4, ka.p, va.p);
+                                             rec_rem.p, rec_rank.p, out.offset.p, vkeys4, ka.p, va.p);
     DCRF_LAUNCHED();
-    table_to_id_kernel<D><<<ceil_div(M, kThreads), kThreads, 0, s>>>(gd, M, d_tab_start.p, vert_rep.p,
-                                                                    slot_of.p, table.p);
+    // Neighbour look-ups go through a second, COMPACT table of vertex ids (capacity = pow2 >= 2 M_b per
+    // image, ~1 MB per VOC image: the batch's tables stay L2 resident), instead of the insertion table
+    // that is sized for the worst case M = E (16 MB per image, every probe a DRAM access).
+    std::vector<int64_t> tab2_start(B + 1, 0);
+    std::vector<int> tab2_mask(B);
+    for (int b = 0; b < B; b++) {
+        const int64_t need = 2 * (int64_t)(h_vs[b + 1] - h_vs[b]);
+        int64_t cap = 64;
+        while (cap < need) cap <<= 1;
+        tab2_mask[b] = (int)(cap - 1);
+        tab2_start[b + 1] = tab2_start[b] + cap;
+    }
+    DevBuf<int64_t> d_tab2_start;
+    DevBuf<int> d_tab2_mask;
+    DevBuf<int32_t> table2;
+    d_tab2_start.alloc(B + 1, s);
+    d_tab2_mask.alloc(B, s);
+    table2.alloc(tab2_start[B], s);
+    DCRF_CUDA(cudaMemcpyAsync(d_tab2_start.p, tab2_start.data(), sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaMemcpyAsync(d_tab2_mask.p, tab2_mask.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(cudaMemsetAsync(table2.p, 0xFF, sizeof(int32_t) * tab2_start[B], s));
+    compact_insert_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
+                                                                    d_tab2_mask.p, vkeys4, table2.p);
     DCRF_LAUNCHED();
 
     out.neigh.alloc((size_t)M * d1, s);
     DCRF_CUDA(cudaMemsetAsync(out.neigh.p, 0xFF, sizeof(int2) * M * d1, s));
     neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
-        M, B, d_vert_start.p, d_tab_start.p, d_tab_mask.p, table.p, vkeys4, out.neigh.p);
+        M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
     DCRF_LAUNCHED();
+    DCRF_CUDA(cudaStreamSynchronize(s));  // tab2_* host vectors are read by the async copies above
 
     // transposed incidence rows: stable sort of entries by vertex id
     kb.alloc(E, s); vb.alloc(E, s);
