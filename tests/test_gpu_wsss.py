@@ -199,6 +199,44 @@ def test_batch_pipeline_matches_blocking_calls():
             assert a.shape == b.shape and np.array_equal(a, b)
 
 
+def test_batch_pipeline_chunked_sub_batches():
+    """chunk_images cuts a batch into sub-batches (own handles, uploads overlapping kernels); every
+    image is an independent CRF, so the results equal the un-chunked call bit for bit."""
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200.pipeline import BatchPipeline, pinned_empty
+
+    cfg = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 40, "bi_srgb": 13, "bi_compat": 10, "iterations": 3}
+    L = 4
+    sizes = [(40 + 3 * i, 30 + (i % 3)) for i in range(7)]
+    imgs = [S.natural_image(h, w, i) for i, (w, h) in enumerate(sizes)]
+    Us = [S.random_unary(L, w * h, 100 + i) for i, (w, h) in enumerate(sizes)]
+    n = sum(w * h for w, h in sizes)
+    U = pinned_empty(n * L)
+    U[:] = np.concatenate([u.ravel() for u in Us])
+    I = pinned_empty(n * 3, np.uint8)
+    I[:] = np.concatenate([im.ravel() for im in imgs])
+    d = G.DenseCRFBatch(sizes, L)
+    d.setUnaryEnergy(Us)
+    d.addPairwiseGaussian(sxy=3, compat=3)
+    d.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs, compat=10)
+    ref_q = d.inference(3)
+    ref_l = [q.argmax(0).astype(np.int32) for q in ref_q]
+    for chunk in (3, 2, 7, 100):
+        outq, outl = pinned_empty(n * L), pinned_empty(n, np.int32)
+        with BatchPipeline(n_slots=3, chunk_images=chunk) as pipe:
+            t1 = pipe.submit(sizes, L, U, I, cfg, out=outq)
+            t2 = pipe.submit(sizes, L, Us, imgs, cfg, out=outl, labels=True)   # per-image lists
+            got_q, got_l = pipe.result(t1), pipe.result(t2)
+        assert len(got_q) == len(got_l) == len(sizes)
+        for a, b in zip(got_q, ref_q):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        for a, b, (w, h) in zip(got_l, ref_l, sizes):
+            assert a.shape == (h, w) and np.array_equal(a.ravel(), b)
+        # the flat output buffer holds the images back to back exactly like the un-chunked call
+        assert np.array_equal(outq, np.concatenate([q.ravel() for q in ref_q]))
+
+
 def test_gpu_unary_construction_matches_numpy():
     """dcrf_set_unary_from_{probs,logits,labels} against pydensecrf.utils-style NumPy unaries: the
     unary is read back through inference(0) = softmax(-U)."""

@@ -28,9 +28,11 @@ namespace {
 struct ThreadStreams {
     cudaStream_t main[64] = {};
     cudaStream_t side[64][kMaxPairwise - 1] = {};
+    cudaStream_t upload[64] = {};
     ~ThreadStreams() {
         for (int d = 0; d < 64; d++) {
             if (main[d]) cudaStreamDestroy(main[d]);
+            if (upload[d]) cudaStreamDestroy(upload[d]);
             for (auto s : side[d])
                 if (s) cudaStreamDestroy(s);
         }
@@ -42,6 +44,11 @@ thread_local ThreadStreams t_streams;
 static cudaStream_t thread_main_stream(int dev) {
     if (!t_streams.main[dev]) DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.main[dev], cudaStreamNonBlocking));
     return t_streams.main[dev];
+}
+static cudaStream_t thread_upload_stream(int dev) {
+    if (!t_streams.upload[dev])
+        DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.upload[dev], cudaStreamNonBlocking));
+    return t_streams.upload[dev];
 }
 static cudaStream_t thread_side_stream(int dev, int k) {
     if (!t_streams.side[dev][k])
@@ -129,6 +136,11 @@ struct dcrf_handle {
     // one (the small, latency-bound Gaussian lattice hides behind the bandwidth-bound bilateral one)
     cudaStream_t side[kMaxPairwise - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxPairwise - 1] = {};
+    // async-host mode: the unary upload (H2D + layout change) runs on the thread's upload stream so
+    // that the lattice builds enqueued next on `stream` overlap it; joined before the unary is read
+    DevBuf<float> upload_stage;
+    cudaEvent_t ev_upload_begin = nullptr, ev_upload_end = nullptr;
+    bool upload_pending = false;
 };
 
 namespace {
@@ -168,6 +180,14 @@ int guarded(F &&f) {
 // end of a call that read or wrote caller HOST memory: block unless the handle is in async-host mode
 void host_sync(dcrf_handle *h) {
     if (!h->async_host) DCRF_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// make `stream` wait for a unary upload still running on the upload stream, then recycle its staging
+void join_upload(dcrf_handle *h) {
+    if (!h->upload_pending) return;
+    DCRF_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upload_end, 0));
+    h->upload_stage.release();
+    h->upload_pending = false;
 }
 
 int64_t total_ln(const dcrf_handle *h) { return h->geom.Ntot * (int64_t)h->L; }
@@ -349,6 +369,7 @@ SliceTerm make_term(Pairwise &p, const float *blurred) {
 
 void start_inference(dcrf_handle *h) {
     DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+    join_upload(h);
     SliceArgs a;
     memset(&a, 0, sizeof(a));
     a.n_terms = 0;
@@ -452,6 +473,11 @@ void dcrf_destroy(dcrf_t *h) {
     try {
         DeviceGuard guard(h->device);
         const double t0 = trace_now();
+        join_upload(h);
+        if (h->ev_upload_begin) {
+            cudaEventDestroy(h->ev_upload_begin);
+            cudaEventDestroy(h->ev_upload_end);
+        }
         h->pw.clear();
         h->unary.release();
         h->Q.release();
@@ -518,6 +544,7 @@ int dcrf_set_option(dcrf_t *h, int option, int value) {
 int dcrf_synchronize(dcrf_t *h) {
     return guarded([&] {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
+        join_upload(h);
         DCRF_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
@@ -527,10 +554,28 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
         DCRF_REQUIRE(h && U, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
         DeviceGuard guard(h->device);
-        DevBuf<float> stage;
-        const float *src = to_device(h, U, (size_t)total_ln(h), on_device, stage);
-        launch_ln_to_pm(src, h->unary.p, h->geom, h->L, h->Lp, h->stream);
-        if (!on_device) host_sync(h);  // caller may reuse U
+        join_upload(h);
+        if (!on_device && h->async_host) {
+            // H2D + layout change on the upload stream; `stream` goes on (lattice builds) meanwhile
+            const cudaStream_t up = thread_upload_stream(h->device);
+            if (!h->ev_upload_begin) {
+                DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_upload_begin, cudaEventDisableTiming));
+                DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_upload_end, cudaEventDisableTiming));
+            }
+            const size_t n = (size_t)total_ln(h);
+            h->upload_stage.alloc(n, h->stream);
+            DCRF_CUDA(cudaEventRecord(h->ev_upload_begin, h->stream));
+            DCRF_CUDA(cudaStreamWaitEvent(up, h->ev_upload_begin, 0));
+            DCRF_CUDA(cudaMemcpyAsync(h->upload_stage.p, U, sizeof(float) * n, cudaMemcpyHostToDevice, up));
+            launch_ln_to_pm(h->upload_stage.p, h->unary.p, h->geom, h->L, h->Lp, up);
+            DCRF_CUDA(cudaEventRecord(h->ev_upload_end, up));
+            h->upload_pending = true;
+        } else {
+            DevBuf<float> stage;
+            const float *src = to_device(h, U, (size_t)total_ln(h), on_device, stage);
+            launch_ln_to_pm(src, h->unary.p, h->geom, h->L, h->Lp, h->stream);
+            if (!on_device) host_sync(h);  // caller may reuse U
+        }
         h->unary_set = true;
         h->q_valid = false;
     });
@@ -543,6 +588,7 @@ int dcrf_set_unary_from_probs(dcrf_t *h, const void *probs, int is_f64, double s
         DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
         DCRF_REQUIRE(scale > 0.0 && scale <= 1.0, DCRF_EINVAL, "`scale` needs to be in (0,1]");
         DeviceGuard guard(h->device);
+        join_upload(h);
         const size_t n = (size_t)total_ln(h);
         const void *src = probs;
         DevBuf<double> stage64;
@@ -563,6 +609,7 @@ int dcrf_set_unary_from_logits(dcrf_t *h, const float *feat, int use_log, int on
         DCRF_REQUIRE(h && feat, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
         DeviceGuard guard(h->device);
+        join_upload(h);
         DevBuf<float> stage;
         const float *src = to_device(h, feat, (size_t)total_ln(h), on_device, stage);
         launch_unary_from_logits(src, h->unary.p, h->geom.Ntot, h->L, h->Lp, use_log, h->stream);
@@ -578,6 +625,7 @@ int dcrf_set_unary_from_labels(dcrf_t *h, const int32_t *labels, float gt_prob, 
         DCRF_REQUIRE(h->L >= 2, DCRF_ESTATE, "unary_from_labels needs at least 2 labels");
         DCRF_REQUIRE(gt_prob > 0.f && gt_prob < 1.f, DCRF_EINVAL, "`gt_prob must be in (0,1).");
         DeviceGuard guard(h->device);
+        join_upload(h);
         DevBuf<int32_t> stage;
         DevBuf<int> bad;
         const int32_t *src = to_device(h, labels, (size_t)h->geom.Ntot, on_device, stage);
@@ -753,6 +801,7 @@ int dcrf_kl_divergence(dcrf_t *h, double *kl_out) {
         DCRF_REQUIRE(h && kl_out, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call startInference first");
         DeviceGuard guard(h->device);
+        join_upload(h);
         cudaStream_t s = h->stream;
         const int64_t Ntot = h->geom.Ntot;
         const bool seq = h->L <= 2;
