@@ -383,6 +383,8 @@ def run_ours(args):
                "sample": "%d VOC-shaped images, one per host thread, oracle restatement of pydensecrf "
                          "(%.2f s wall)" % (n_img, dt),
                "images_per_s": n_img / dt}
+        dt1 = cpu_sample(1, 1)   # the same port on ONE core
+        cpu["single_core"] = {"value": N * N_ITER / dt1 / 1e6, "unit": UNIT, "images_per_s": 1.0 / dt1}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

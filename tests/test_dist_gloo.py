@@ -38,6 +38,12 @@ def _worker(rank, world, port, q):
     for i in E.shard_indices(len(gts), rank, world):
         conf += O.confusion(gts[i], preds[i], C_)
     total = E.all_reduce_confusion_host(conf)
+    # same sweep with the shards balanced by pixel count instead of strided
+    conf_b = np.zeros((C_ + 1, C_), np.int64)
+    for i in E.shard_balanced([g.size for g in gts], rank, world):
+        conf_b += O.confusion(gts[i], preds[i], C_)
+    total_b = E.all_reduce_confusion_host(conf_b)
+    assert np.array_equal(total, total_b)
     q.put((rank, total.tolist()))
     dist.destroy_process_group()
 

@@ -94,6 +94,19 @@ def test_miou_conventions():
     assert np.array_equal(iou2, riou2) and miou2 == rmiou2
 
 
+def test_shard_balanced_partitions_and_balances():
+    rng = np.random.default_rng(3)
+    counts = rng.choice([500 * 375, 375 * 500, 500 * 333, 500 * 500, 334 * 500, 2448 * 2448], size=203)
+    for world in (1, 2, 3, 8):
+        shards = [E.shard_balanced(counts, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(len(counts)))          # a partition
+        assert all(s == sorted(s) for s in shards)
+        loads = [int(sum(counts[i] for i in s)) for s in shards]
+        assert max(loads) - min(loads) <= int(counts.max())                 # LPT bound
+    assert E.shard_balanced([5, 5, 5, 5], 0, 2) == [0, 2] and E.shard_balanced([5, 5, 5, 5], 1, 2) == [1, 3]
+    assert E.shard_balanced([], 0, 4) == []
+
+
 def test_shard_indices_stride():
     assert E.shard_indices(10, 1, 4) == [1, 5, 9]
     allidx = sorted(sum((E.shard_indices(1449, r, 8) for r in range(8)), []))

@@ -155,3 +155,20 @@ def shard_indices(n_items, rank, world_size):
     """Item i -> rank i mod world_size: the `split_dataset` striding of
     /root/reference/03b_irn/step/cam_to_ir_label.py:114-117."""
     return list(range(rank, n_items, world_size))
+
+
+def shard_balanced(pixel_counts, rank, world_size):
+    """Length-balanced alternative for mixed image sizes: items are dealt in
+    decreasing pixel count to the currently lightest rank (ties: lowest rank, lowest index), the
+    same deterministic assignment on every rank; returns this rank's indices in ascending order.
+    The confusion matrix is a sum over images, so any assignment gives the same all-reduced result."""
+    counts = [int(c) for c in pixel_counts]
+    order = sorted(range(len(counts)), key=lambda i: (-counts[i], i))
+    load = [0] * int(world_size)
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        load[r] += counts[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)

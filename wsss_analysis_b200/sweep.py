@@ -17,7 +17,7 @@ import numpy as np
 
 from . import synthetic
 from .densecrf import DenseCRFBatch
-from .evaluation import ConfusionAccumulator, iou_irn, iou_sec, shard_indices
+from .evaluation import ConfusionAccumulator, iou_irn, iou_sec, shard_balanced, shard_indices
 
 VOC_CRF = dict(g_sxy=3, g_compat=3, bi_sxy=80, bi_srgb=13, bi_compat=10, iterations=10)  # SEC.py:20
 
@@ -38,12 +38,15 @@ def synthetic_item(i, n_labels, seed=0):
 
 
 def run_sweep(items, n_labels, rank=0, world_size=1, batch=16, crf=VOC_CRF, device=None, all_reduce=True,
-              item_fn=None):
+              item_fn=None, pixel_counts=None):
     """items: number of images (synthetic) or a list of (img, unary, gt) tuples.
     Returns dict(confusion (C+1, C) int64, miou_irn, miou_sec, images (this rank), seconds)."""
     n_items = items if isinstance(items, int) else len(items)
     get = (item_fn or (lambda i: synthetic_item(i, n_labels))) if isinstance(items, int) else (lambda i: items[i])
-    mine = shard_indices(n_items, rank, world_size)
+    # striding (the reference's split_dataset convention) unless per-item pixel counts are given,
+    # in which case the shards are balanced by pixel count
+    mine = (shard_indices(n_items, rank, world_size) if pixel_counts is None
+            else shard_balanced(pixel_counts, rank, world_size))
     acc = ConfusionAccumulator(n_labels, device=device)
     seconds = 0.0  # CRF + confusion only; fetching / synthesising the inputs is not part of the path
     for b0 in range(0, len(mine), batch):
