@@ -70,6 +70,10 @@ def cpu_one_image(args):
     return d.inference(N_ITER)
 
 
+# measured LSU row-gather ceiling (tools/micro/bulk_gather.cu, profiles/r1_micro_gather.txt)
+GATHER_CEILING_GROWS = 106.7
+
+
 def cpu_sample(n_images, threads):
     """Wall time of `n_images` VOC-shaped CRFs over `threads` host threads (ctypes drops the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -349,8 +353,17 @@ def run_ours(args):
             else:
                 by = algorithmic_bytes(cls, tag, Ntot, L_LAB, lattice_M[tag])
                 name = "%s_kernel d=%d" % (cls, tag)
+            # row gathers per launch (one 96-byte row per lattice entry): the splat gathers E = N(d+1)
+            # pixel rows, the fused slice E_gauss + E_bilat vertex rows; compared below with the
+            # measured LSU gather ceiling of tools/micro/bulk_gather.cu
+            rows = None
+            if cls == "slice":
+                rows = sum(Ntot * (d + 1) for d in lattice_M)
+            elif cls == "splat":
+                rows = Ntot * (tag + 1)
             kernels.append({"kernel": name, "launches": n, "total_ms": ms, "avg_us": ms / n * 1e3,
-                            "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms / n * 1e-3) / 1e9})
+                            "algorithmic_bytes_per_launch": by, "achieved_gbs": by / (ms / n * 1e-3) / 1e9,
+                            "gather_rows_per_launch": rows})
     kernels.sort(key=lambda k: -k["total_ms"])
     top = kernels[0]
     kernel_ms = sum(k["total_ms"] for k in kernels)
@@ -370,7 +383,15 @@ def run_ours(args):
                   "serialised vs %.2f ms/step timed)" % (args.steps, ms_prof / args.steps, ms_dev / args.steps),
         "per_kernel": [{"kernel": k["kernel"], "launches": k["launches"], "avg_us": round(k["avg_us"], 2),
                         "achieved_gbs": round(k["achieved_gbs"], 1), "frac": round(k["achieved_gbs"] / peak, 4),
-                        "share_of_step": round(k["total_ms"] / ms_prof, 4)} for k in kernels],
+                        "share_of_step": round(k["total_ms"] / ms_prof, 4),
+                        "gather_grows_per_s": (None if not k["gather_rows_per_launch"] else
+                                               round(k["gather_rows_per_launch"] / (k["avg_us"] * 1e-6) / 1e9, 1)),
+                        "gather_frac_of_lsu_ceiling": (None if not k["gather_rows_per_launch"] else round(
+                            k["gather_rows_per_launch"] / (k["avg_us"] * 1e-6) / 1e9 / GATHER_CEILING_GROWS, 3))}
+                       for k in kernels],
+        "gather_ceiling": {"value": GATHER_CEILING_GROWS, "unit": "G rows/s (96-byte rows, LDG.128 by 6-lane groups)",
+                           "source": "tools/micro/bulk_gather.cu measured on B200 (L1- or L2-resident table, "
+                                     "same rate); profiles/r1_micro_gather.txt"},
         "iteration_kernels_share_of_step": kernel_ms / ms_prof,
     }
 
