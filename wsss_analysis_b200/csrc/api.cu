@@ -341,7 +341,7 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         norm.alloc(bg.Ntot, s);
         launch_kernel_norm(lat, bg.Ntot, ntype, norm.p, s);
     }
-    launch_pack_fast_tables(lat, pre_norm(ntype) ? norm.p : nullptr, s);
+    launch_pack_fast_tables(lat, pre_norm(ntype) ? norm.p : nullptr, post_norm(ntype) ? norm.p : nullptr, s);
     if (uniform) {
         if (norm.p) p->norm.alloc(Ntot, s);
         launch_replicate_lattice(single, norm.p, h->geom.B, bg.Ntot, p->lat, p->norm.p, s);

@@ -158,7 +158,7 @@ struct Lattice {
     DevBuf<int32_t> csr_pix;       // [E] pixel of each sorted entry (ascending entry order per row)
     DevBuf<float> csr_w;           // [E] barycentric weight of each sorted entry
     // packed tables of the fast path (one 64-bit load per entry instead of two 32-bit loads)
-    DevBuf<int2> ent;              // [E] (vertex id, barycentric weight bits) of entry e
+    DevBuf<int2> ent;              // [E] (vertex id, weight * post-norm[pixel] bits) of entry e
     DevBuf<int2> csr_ent;          // [E] (pixel, weight * pre-norm[pixel] bits) of each sorted entry
     DevBuf<int> row_counter;       // [1] dynamic row-chunk dispenser of the fast splat
     DevBuf<int32_t> long_rows;     // rows with more than kSplatLongRow entries (tail summed by a whole CTA)
@@ -197,8 +197,9 @@ struct SliceArgs {
 // values <- splat of (pre ? norm (.) Q : Q)       (A.4 splat, A.5 pre-scaling)
 void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, float *val, int Lp,
                   cudaStream_t s);
-// fast path: packed tables, weights pre-multiplied by the pre-normalisation, FMA accumulation
-void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s);
+// fast path: packed tables; splat weights pre-multiplied by the pre-normalisation, slice weights by
+// the post-normalisation (the fast kernels never read the norm vector), FMA accumulation
+void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *norm_post, cudaStream_t s);
 void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s);
 void launch_find_long_rows(Lattice &lat, cudaStream_t s);
 // out <- in + 0.5 (in[n1] + in[n2]) along axis j  (A.4 blur)

@@ -142,11 +142,13 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) pack_fast_tables_kernel(
     const int32_t *__restrict__ offset, const float *__restrict__ bary, const int32_t *__restrict__ csr_pix,
-    const float *__restrict__ csr_w, const float *__restrict__ norm_pre, int2 *__restrict__ ent,
-    int2 *__restrict__ csr_ent, int64_t E) {
+    const float *__restrict__ csr_w, const float *__restrict__ norm_pre, const float *__restrict__ norm_post,
+    int d1, int2 *__restrict__ ent, int2 *__restrict__ csr_ent, int64_t E) {
     const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (e >= E) return;
-    ent[e] = make_int2(offset[e], __float_as_int(bary[e]));
+    float b = bary[e];
+    if (norm_post) b = __fmul_rn(b, norm_post[e / d1]);  // post-normalisation folded into the slice weight
+    ent[e] = make_int2(offset[e], __float_as_int(b));
     const int p = csr_pix[e];
     float w = csr_w[e];
     if (norm_pre) w = __fmul_rn(w, norm_pre[p]);
@@ -262,6 +264,106 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
         cnt_cur = ncnt;
 #pragma unroll
         for (int i = 0; i < SB; i++) e_cur[i] = e_next[i];
+        if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
+    }
+}
+
+// Same schedule with COOPERATIVE entry loads: every warp-level load request costs the LSU a fixed
+// >= 6 cycles however few bytes it moves (tools/micro/bulk_gather.cu), and above each lane loads all
+// SB entries of its group's batch itself -- SB broadcast requests per SB gathers.  Here lane c of a
+// group loads entry c of the batch (one request per G entries) and the (pixel, weight) pairs are
+// broadcast inside the group with shuffles.  A trip handles NB * G entries.  Summation order and
+// arithmetic are unchanged, so the result is bit-identical to splat_fast_kernel.
+template <int G, int NB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
+                                                              const int2 *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M,
+                                                              int *__restrict__ row_counter) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int SB = G * NB;
+    constexpr int gpw = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int c = lane - sub * G;
+    const bool lane_on = sub < gpw;
+    const int gbase = (sub * G) & 31;
+    const unsigned leader_bit = 1u << gbase;
+    int q_base = 0, q_next = 0, q_end = 0;
+    int bounds = 0, bound_last = 0;
+    bool exhausted = false;
+    int v = -1, s = 0, s1 = 0, cnt_cur = 0;
+    int2 e_cur[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) e_cur[b] = make_int2(0, 0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (;;) {
+        // 1. broadcast the batch's entries inside the group, request the row gathers
+        float4 q[SB];
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int i = 0; i < G; i++) {
+                const int k = b * G + i;
+                const int px = __shfl_sync(FULL, e_cur[b].x, (gbase + i) & 31);
+                q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < cnt_cur) q[k] = __ldg(Q4 + ((unsigned)px * G + c));
+            }
+        // 2. next batch: same row, or a new row from the warp's chunk
+        const bool row_ends = v < 0 || s + SB >= s1;
+        int nv = v, ns = s + SB, ns1 = s1;
+        const bool need = lane_on && row_ends;
+        const unsigned need_mask = __ballot_sync(FULL, need && c == 0);
+        if (need_mask) {
+            if (q_next >= q_end && !exhausted) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(row_counter, kSplatChunk);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= M) {
+                    exhausted = true;
+                } else {
+                    q_base = q_next = base;
+                    q_end = min(base + kSplatChunk, M);
+                    bounds = csr_start[min(base + lane, M)];
+                    bound_last = csr_start[q_end];
+                }
+            }
+            const int rank = __popc(need_mask & (leader_bit - 1));
+            const int row = q_next + rank;
+            const bool take = need && row < q_end;
+            const int rel = take ? row - q_base : 0;
+            const int b0 = __shfl_sync(FULL, bounds, rel & 31);
+            int b1 = __shfl_sync(FULL, bounds, (rel + 1) & 31);
+            if (rel + 1 == q_end - q_base) b1 = bound_last;
+            if (need) {
+                nv = take ? row : -1;
+                ns = b0;
+                ns1 = min(b1, b0 + kSplatLongRow);
+            }
+            q_next = min(q_end, q_next + __popc(need_mask));
+        }
+        // 3. cooperative entry loads of the next batch: lane c takes entries c, c + G, ...
+        const int ncnt = nv >= 0 ? min(SB, ns1 - ns) : 0;
+        int2 e_next[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            e_next[b] = (b * G + c < ncnt) ? __ldg(csr_ent + ns + b * G + c) : make_int2(0, 0);
+        // 4. consume (padded slots add 0 * 0)
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int i = 0; i < G; i++)
+                fma4(acc, __int_as_float(__shfl_sync(FULL, e_cur[b].y, (gbase + i) & 31)), q[b * G + i]);
+        if (v >= 0 && row_ends) {
+            val4[(unsigned)v * G + c] = acc;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        v = nv;
+        s = ns;
+        s1 = ns1;
+        cnt_cur = ncnt;
+#pragma unroll
+        for (int b = 0; b < NB; b++) e_cur[b] = e_next[b];
         if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
     }
 }
@@ -585,8 +687,9 @@ __device__ __forceinline__ float4 slice_fast_row(const int2 *__restrict__ ent, c
 
 // (register budget: the default heuristic's 32 registers / full occupancy is fastest -- 590 us;
 // forcing 40 / 48 / 64 registers to keep more gathers in flight per thread gave 596 / 602 / 654 us)
+// __launch_bounds__(.., 8): 32 registers = full occupancy; at 34 (6 resident CTAs) it takes 639 us.
 template <int G, int DA, int DB>
-__global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const SliceArgs a,
+__global__ void __launch_bounds__(kThreads, 2048 / kThreads) slice_softmax_fast_kernel(const SliceArgs a,
                                                                       const float4 *__restrict__ unary4,
                                                                       float4 *__restrict__ Q4, unsigned Ntot,
                                                                       int L, int g_rt) {
@@ -600,9 +703,8 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_kernel(const Slic
     const float4 x0 = slice_fast_row<DA>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, g, c);
     const float4 x1 = slice_fast_row<DB>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, g, c);
     const float4 u = __ldg(unary4 + (p * g + c));
-    float w0 = t0.potts_w * t0.alpha, w1 = t1.potts_w * t1.alpha;
-    if (t0.norm) w0 *= __ldg(t0.norm + p);
-    if (t1.norm) w1 *= __ldg(t1.norm + p);
+    // (the per-pixel post-normalisation is already inside the packed entry weights)
+    const float w0 = t0.potts_w * t0.alpha, w1 = t1.potts_w * t1.alpha;
     float4 t;
     t.x = fmaf(w1, x1.x, fmaf(w0, x0.x, -u.x));
     t.y = fmaf(w1, x1.y, fmaf(w0, x0.y, -u.y));
@@ -656,8 +758,7 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_generic_kernel(co
             const int2 e = __ldg(ep + r);
             fma4(acc, __int_as_float(e.y), __ldg(val4 + ((unsigned)e.x * g + c)));
         }
-        float w = tm.potts_w * tm.alpha;
-        if (tm.norm) w *= __ldg(tm.norm + p);
+        const float w = tm.potts_w * tm.alpha;  // post-normalisation: inside the entry weights
         t.x = fmaf(w, acc.x, t.x);
         t.y = fmaf(w, acc.y, t.y);
         t.z = fmaf(w, acc.z, t.z);
@@ -1086,14 +1187,15 @@ void launch_find_long_rows(Lattice &lat, cudaStream_t s) {
     DCRF_LAUNCHED();
 }
 
-void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, cudaStream_t s) {
+void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *norm_post, cudaStream_t s) {
     if (lat.E == 0) return;
     lat.ent.alloc(lat.E, s);
     lat.csr_ent.alloc(lat.E, s);
     lat.row_counter.alloc(1, s);
     launch_find_long_rows(lat, s);
     pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
-        lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, lat.ent.p, lat.csr_ent.p, lat.E);
+        lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, norm_post, lat.d + 1, lat.ent.p,
+        lat.csr_ent.p, lat.E);
     DCRF_LAUNCHED();
 }
 
@@ -1112,6 +1214,32 @@ void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, c
     // entries per trip: long rows (Gaussian lattice, ~23 entries) amortise the loop overhead over 8
     // entries, short skewed rows (bilateral lattice, median 6) waste fewer predicated slots with 4
     const bool long_rows = lat.E >= 16 * lat.M;
+    // 4 <= G <= 8 (13..32 labels): cooperative entry loads, G entries per trip (bilateral splat of the
+    // VOC batch: 417 us against 463 us for splat_fast_kernel<6, 4>, Gaussian 206 against 218 <6, 8>)
+    if (g >= 4 && g <= 8) {
+        const float4 *q4 = reinterpret_cast<const float4 *>(Q);
+        float4 *v4 = reinterpret_cast<float4 *>(val);
+#define DCRF_COOP_LAUNCH(GG, MINB)                                                                          \
+    case GG: {                                                                                              \
+        static const int per_sm = resident_blocks_per_sm(splat_coop_kernel<GG, 1, MINB>);                   \
+        const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);   \
+        splat_coop_kernel<GG, 1, MINB><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_ent.p, q4, v4,     \
+                                                               (int)lat.M, lat.row_counter.p);             \
+        splat_long_tail_kernel<GG><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(               \
+            lat.csr_start.p, lat.csr_ent.p, q4, v4, lat.long_rows.p, lat.n_long.p, g);                     \
+    } break;
+        switch (g) {
+            DCRF_COOP_LAUNCH(4, 5)
+            DCRF_COOP_LAUNCH(5, 5)
+            DCRF_COOP_LAUNCH(6, 5)
+            DCRF_COOP_LAUNCH(7, 4)
+            DCRF_COOP_LAUNCH(8, 4)
+        }
+#undef DCRF_COOP_LAUNCH
+        DCRF_LAUNCHED();
+        g_launches.fetch_add(1);
+        return;
+    }
     DCRF_DISPATCH_G(g, {
         // persistent grid of exactly one resident wave; rows are claimed dynamically
         if (long_rows) {
