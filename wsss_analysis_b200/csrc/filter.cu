@@ -685,11 +685,39 @@ __device__ __forceinline__ float4 slice_fast_row(const int2 *__restrict__ ent, c
     return acc;
 }
 
+// Cooperative form of slice_fast_row: lane c of the pixel's group loads entries c, c + G, ... (one load
+// request for the group instead of one broadcast request per 16 bytes of entries) and the (vertex,
+// weight) pairs travel by shuffle.  Same values, same order of additions.
+template <int D, int G>
+__device__ __forceinline__ float4 slice_fast_row_coop(const int2 *__restrict__ ent, const float4 *__restrict__ val4,
+                                                      unsigned p, unsigned c, int gbase) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NL = (D + G) / G;
+    int2 e[NL];
+    const int2 *ep = ent + (size_t)p * (D + 1);
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        const int idx = (int)c + j * G;
+        e[j] = idx <= D ? __ldg(ep + idx) : make_int2(0, 0);
+    }
+    float4 v[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        const unsigned vx = (unsigned)__shfl_sync(FULL, e[r / G].x, (gbase + r % G) & 31);
+        v[r] = __ldg(val4 + (vx * G + c));
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r <= D; r++)
+        fma4(acc, __int_as_float(__shfl_sync(FULL, e[r / G].y, (gbase + r % G) & 31)), v[r]);
+    return acc;
+}
+
 // (register budget: the default heuristic's 32 registers / full occupancy is fastest -- 590 us;
 // forcing 40 / 48 / 64 registers to keep more gathers in flight per thread gave 596 / 602 / 654 us)
 // __launch_bounds__(.., 8): 32 registers = full occupancy; at 34 (6 resident CTAs) it takes 639 us.
 template <int G, int DA, int DB>
-__global__ void __launch_bounds__(kThreads, 2048 / kThreads) slice_softmax_fast_kernel(const SliceArgs a,
+__global__ void __launch_bounds__(kThreads, G ? 2048 / kThreads : 1) slice_softmax_fast_kernel(const SliceArgs a,
                                                                       const float4 *__restrict__ unary4,
                                                                       float4 *__restrict__ Q4, unsigned Ntot,
                                                                       int L, int g_rt) {
@@ -700,8 +728,15 @@ __global__ void __launch_bounds__(kThreads, 2048 / kThreads) slice_softmax_fast_
     const unsigned p = act ? (unsigned)p64 : 0u;
     const SliceTerm &t0 = a.term[0];
     const SliceTerm &t1 = a.term[1];
-    const float4 x0 = slice_fast_row<DA>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, g, c);
-    const float4 x1 = slice_fast_row<DB>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, g, c);
+    float4 x0, x1;
+    if (G >= 3) {  // cooperative entry loads (580 -> 567 us at G = 6, bit-identical)
+        const int gb = (int)(threadIdx.x & 31) - (int)c;
+        x0 = slice_fast_row_coop<DA, (G >= 3 ? G : 3)>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, c, gb);
+        x1 = slice_fast_row_coop<DB, (G >= 3 ? G : 3)>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, c, gb);
+    } else {
+        x0 = slice_fast_row<DA>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, g, c);
+        x1 = slice_fast_row<DB>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, g, c);
+    }
     const float4 u = __ldg(unary4 + (p * g + c));
     // (the per-pixel post-normalisation is already inside the packed entry weights)
     const float w0 = t0.potts_w * t0.alpha, w1 = t1.potts_w * t1.alpha;
