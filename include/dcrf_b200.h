@@ -167,6 +167,13 @@ int dcrf_start_inference(dcrf_t *h);
 int dcrf_step_inference(dcrf_t *h);
 int dcrf_get_q(dcrf_t *h, float *Q_out, int on_device);
 int dcrf_set_q(dcrf_t *h, const float *Q_in, int on_device);
+
+/* The running Q as concatenated (H_b, W_b, L) float32 blocks -- the layout [EXT] lib/crf.py's
+ * crf_inference returns to 03a_sec-dsrg/SEC.py:275 and model.py:689-693 -- without a host transpose.
+ * min_prob > 0 additionally applies the epilogue of the `crf` py_func closure (SEC.py:277-278,
+ * DSRG.py:330-331): ret[ret < min_prob] = min_prob; ret /= sum over labels (NumPy's float32
+ * summation order, bit-identical); take_log != 0 then takes the logarithm (SEC.py:279). */
+int dcrf_get_q_hwc(dcrf_t *h, float min_prob, int take_log, float *out, int on_device);
 int dcrf_kl_divergence(dcrf_t *h, double *kl_out); /* of the running Q; batch-of-one only */
 
 /* ---- introspection (bit-exact lattice tests) ------------------------- */

@@ -107,6 +107,46 @@ def test_crf_inference_and_sec_layer():
     assert np.abs(np.exp(got) - np.exp(ref)).max() <= 1e-4
 
 
+def test_marginals_hwc_and_sec_epilogue_match_numpy():
+    """dcrf_get_q_hwc: the (H, W, C) layout is a pure re-arrangement of inference()'s output (bit for
+    bit); with min_prob the clamp + renormalisation equal the NumPy lines of SEC.py:277-278 bit for bit
+    (the kernel follows NumPy's float32 summation order), and the log agrees within float rounding."""
+    import torch
+
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+
+    for L in (21, 5, 8, 2, 37):
+        sizes = [(41, 41), (23, 17), (1, 9)]
+        imgs = [S.natural_image(h, w, 3 + i) for i, (w, h) in enumerate(sizes)]
+        Us = [S.random_unary(L, w * h, 7 + i) * 3 for i, (w, h) in enumerate(sizes)]   # peaky: many Q < 1e-4
+        d = G.DenseCRFBatch(sizes, L)
+        d.setUnaryEnergy(Us)
+        d.addPairwiseGaussian(sxy=3 / 12, compat=3)
+        d.addPairwiseBilateral(sxy=80 / 12, srgb=13, rgbim=imgs, compat=10)
+        d.run(5)
+        Q = d.marginals()
+        hwc = d.marginals_hwc()
+        clamped = d.marginals_hwc(min_prob=1e-4)
+        logged = d.marginals_hwc(min_prob=1e-4, log=True)
+        dev = d.marginals_hwc_device(min_prob=1e-4, log=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(dev.cpu().numpy(), np.concatenate([x.ravel() for x in logged]))
+        n_clamped = 0
+        for q, a, c, lg, (w, h) in zip(Q, hwc, clamped, logged, sizes):
+            ref = np.ascontiguousarray(np.transpose(q.reshape(L, h, w), (1, 2, 0)))
+            assert a.shape == (h, w, L) and np.array_equal(a, ref)
+            ret = ref.copy()[None]
+            n_clamped += int((ret < 1e-4).sum())
+            ret[ret < 1e-4] = 1e-4
+            ret /= np.sum(ret, axis=3, keepdims=True)
+            assert np.array_equal(c, ret[0])
+            np.testing.assert_allclose(lg, np.log(ret[0]), rtol=0, atol=2e-6)
+        if L >= 5:
+            assert n_clamped > 0
+        d.close()
+
+
 def test_crf_inference_label_drop_in():
     from oracle import oracle as O
     from wsss_analysis_b200 import synthetic as S

@@ -41,6 +41,7 @@ SIGNATURES = {
     "dcrf_start_inference": (_i, [_vp]),
     "dcrf_step_inference": (_i, [_vp]),
     "dcrf_get_q": (_i, [_vp, _vp, _i]),
+    "dcrf_get_q_hwc": (_i, [_vp, _f, _i, _vp, _i]),
     "dcrf_set_q": (_i, [_vp, _vp, _i]),
     "dcrf_kl_divergence": (_i, [_vp, C.POINTER(C.c_double)]),
     "dcrf_num_pairwise": (_i, [_vp, C.POINTER(_i)]),

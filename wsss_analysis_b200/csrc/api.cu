@@ -783,6 +783,26 @@ int dcrf_get_q(dcrf_t *h, float *Q_out, int on_device) {
     });
 }
 
+int dcrf_get_q_hwc(dcrf_t *h, float min_prob, int take_log, float *out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call startInference first");
+        DCRF_REQUIRE(!(min_prob > 0.f) || min_prob < 1.f, DCRF_EINVAL, "min_prob must be below 1");
+        DeviceGuard guard(h->device);
+        const int64_t n = total_ln(h);
+        const int renorm = min_prob > 0.f ? 1 : 0;
+        if (on_device) {
+            launch_q_to_hwc(h->Q.p, out, h->geom.Ntot, h->L, h->Lp, min_prob, renorm, take_log, h->stream);
+        } else {
+            DevBuf<float> stage;
+            stage.alloc(n, h->stream);
+            launch_q_to_hwc(h->Q.p, stage.p, h->geom.Ntot, h->L, h->Lp, min_prob, renorm, take_log, h->stream);
+            DCRF_CUDA(cudaMemcpyAsync(out, stage.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+            host_sync(h);
+        }
+    });
+}
+
 int dcrf_set_q(dcrf_t *h, const float *Q_in, int on_device) {
     return guarded([&] {
         DCRF_REQUIRE(h && Q_in, DCRF_EINVAL, "NULL argument");

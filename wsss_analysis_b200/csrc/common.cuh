@@ -225,6 +225,10 @@ void launch_unary_from_logits(const float *feat, float *pm, int64_t Ntot, int L,
 void launch_unary_from_labels(const int32_t *labels, float *pm, int64_t Ntot, int L, int Lp, float n_energy,
                               float p_energy, float unsure_energy, int zero_unsure, int *bad, cudaStream_t s);
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s);
+// out[p * L + l] = Q (pixel-major without padding, the (H, W, C) layout), optionally clamped to
+// >= min_prob and renormalised over labels in NumPy's summation order, optionally log
+void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, float min_prob, int renorm,
+                     int take_log, cudaStream_t s);
 // deterministic double-precision KL terms
 void launch_kl(const float *Q, const float *unary, const float *const *pair_out, int n_pair,
                int64_t Ntot, int L, int Lp, double *out, cudaStream_t s);

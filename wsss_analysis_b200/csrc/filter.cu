@@ -1430,6 +1430,57 @@ void launch_pm_to_ln(const float *pm, float *ln, const BatchGeom &g, int L, int 
     DCRF_LAUNCHED();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Q -> (pixel, label) rows without padding = the (H, W, C) layout SEC / DSRG's crf_inference returns,
+// optionally with the epilogue of their `crf` closure (/root/reference/03a_sec-dsrg/SEC.py:277-279):
+//   ret[ret < min_prob] = min_prob;  ret /= np.sum(ret, axis=3, keepdims=True);  ret = np.log(ret)
+// The sum follows NumPy's float32 pairwise order for n <= 128 (8 strided partial sums combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), remainder added in sequence; plain loop below 8), so clamp,
+// sum and quotient are bit-identical to NumPy; only logf differs from NumPy's SIMD log (<= 2 ulp).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_lo(float v, float lo) { return v < lo ? lo : v; }
+
+__global__ void __launch_bounds__(kThreads) q_to_hwc_kernel(const float *__restrict__ pm, float *__restrict__ out,
+                                                            int64_t total, int L, int Lp, float min_prob,
+                                                            int renorm, int take_log) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= total) return;
+    const int64_t p = i / L;
+    const int l = (int)(i - p * L);
+    const float *row = pm + p * Lp;
+    float v = row[l];
+    if (renorm) {
+        v = clamp_lo(v, min_prob);
+        float sum;
+        if (L < 8) {
+            sum = 0.f;
+            for (int k = 0; k < L; k++) sum = __fadd_rn(sum, clamp_lo(row[k], min_prob));
+        } else {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = clamp_lo(row[j], min_prob);
+            int k = 8;
+            for (; k < L - (L % 8); k += 8)
+#pragma unroll
+                for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], clamp_lo(row[k + j], min_prob));
+            sum = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                            __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+            for (; k < L; k++) sum = __fadd_rn(sum, clamp_lo(row[k], min_prob));
+        }
+        v = __fdiv_rn(v, sum);
+    }
+    if (take_log) v = logf(v);
+    out[i] = v;
+}
+
+void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, float min_prob, int renorm,
+                     int take_log, cudaStream_t s) {
+    if (Ntot == 0) return;
+    const int64_t total = Ntot * L;
+    q_to_hwc_kernel<<<ceil_div(total, kThreads), kThreads, 0, s>>>(pm, out, total, L, Lp, min_prob, renorm, take_log);
+    DCRF_LAUNCHED();
+}
+
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s) {
     if (Ntot == 0) return;
     argmax_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(pm, labels, Ntot, L, Lp);

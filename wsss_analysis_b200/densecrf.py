@@ -480,6 +480,29 @@ class DenseCRFBatch(_Model):
         _lib.check(self._lib.dcrf_get_q(self._h, flat.ctypes.data, 0))
         return self._split(flat, self._L, lambda b: (self._L, int(self._npix[b])))
 
+    def marginals_hwc(self, out=None, min_prob=None, log=False):
+        """Download the running Q as a list of (H_b, W_b, L) float32 arrays -- the layout SEC / DSRG's
+        `crf_inference` returns (03a_sec-dsrg/SEC.py:275) -- with no host transpose.  `min_prob`
+        applies `ret[ret < min_prob] = min_prob; ret /= ret.sum(-1, keepdims=True)` and `log` the
+        final `np.log` of the `crf` closure (SEC.py:277-279) on the GPU."""
+        flat = np.empty(self._Ntot * self._L, np.float32) if out is None else out
+        assert flat.dtype == np.float32 and flat.size == self._Ntot * self._L and flat.flags.c_contiguous
+        flat = flat.reshape(-1)
+        _lib.check(self._lib.dcrf_get_q_hwc(self._h, float(min_prob) if min_prob else 0.0, 1 if log else 0,
+                                            flat.ctypes.data, 0))
+        return self._split(flat, self._L, lambda b: (self._sizes[b][1], self._sizes[b][0], self._L))
+
+    def marginals_hwc_device(self, out=None, min_prob=None, log=False):
+        """Same, into a float32 CUDA tensor of Ntot * L elements (images back to back)."""
+        import torch
+
+        if out is None:
+            out = torch.empty((self._Ntot * self._L,), dtype=torch.float32, device="cuda:%d" % self._dev_index())
+        _lib.check(self._lib.dcrf_get_q_hwc(self._h, float(min_prob) if min_prob else 0.0, 1 if log else 0,
+                                            out.data_ptr(), 1))
+        self._sync_unless_async()
+        return out
+
     def labels(self, out=None):
         """Download argmax of the running Q -> list of (H_b, W_b) int32 label maps."""
         flat = np.empty(self._Ntot, np.int32) if out is None else out

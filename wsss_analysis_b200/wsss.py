@@ -111,9 +111,11 @@ def _unary_from_featmap(feat, use_log):
     return np.copy(unary, order="C").astype(np.float32, copy=False)
 
 
-def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, device=None):
+def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, device=None, min_prob=None,
+                        log=False):
     """Batched `crf_inference`: imgs list of (H_b, W_b, 3) uint8, featmaps list of (H_b, W_b, C).
-    Returns a list of (H_b, W_b, C) float32 marginals."""
+    Returns a list of (H_b, W_b, C) float32 marginals (written in that layout by the GPU).
+    `min_prob` / `log`: the clamp + renormalise + log epilogue of the SEC / DSRG `crf` closure."""
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     out = [None] * len(imgs)
     for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
@@ -124,10 +126,11 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
         d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
                                rgbim=[np.ascontiguousarray(imgs[i], dtype=np.uint8) for i in idx],
                                compat=crf_config["bi_compat"])
-        Q = d.inference(crf_config["iterations"])
+        d.run(crf_config["iterations"])
+        Q = d.marginals_hwc(min_prob=min_prob, log=log)
         d.close()
-        for i, q, (w, h) in zip(idx, Q, sizes):
-            out[i] = np.transpose(q.reshape((num_classes, h, w)), (1, 2, 0))
+        for i, q in zip(idx, Q):
+            out[i] = q
     return out
 
 
@@ -145,15 +148,15 @@ def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, devic
     featemap = np.asarray(featemap)
     batch_size = featemap.shape[0]
     image = np.asarray(image).astype(np.uint8)
-    ret = np.zeros(featemap.shape, dtype=np.float32)
+    # clamp (>= min_prob), renormalisation over classes and log run on the GPU (dcrf_get_q_hwc); the
+    # clamp, the sum (NumPy's float32 order) and the quotient are bit-identical to the NumPy lines
     out = crf_inference_batch([image[i] for i in range(batch_size)], crf_config, num_classes,
-                              [featemap[i] for i in range(batch_size)], use_log=True, device=device)
+                              [featemap[i] for i in range(batch_size)], use_log=True, device=device,
+                              min_prob=min_prob, log=True)
+    ret = np.zeros(featemap.shape, dtype=np.float32)
     for i in range(batch_size):
         ret[i, :, :, :] = out[i]
-    ret[ret < min_prob] = min_prob
-    ret /= np.sum(ret, axis=3, keepdims=True)
-    ret = np.log(ret)
-    return ret.astype(np.float32)
+    return ret
 
 
 def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None,
