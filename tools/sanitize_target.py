@@ -17,6 +17,14 @@ batch([(48, 36)] * 3, 21)                                   # uniform: replicate
 batch([(48, 36), (30, 50)], 6)                              # mixed sizes
 batch([(64, 64)], 21, [np.full((64, 64, 3), 90, np.uint8)]) # flat: long-row tail kernel
 batch([(40, 30)], 2); batch([(40, 30)], 1); batch([(20, 20)], 37); batch([(40, 30)], 5, exact=True)
+for L_ in (13, 16, 20, 24, 28, 32):                          # cooperative splat / slice at G = 4, 5, 6, 7, 8
+    batch([(30, 20), (17, 25)], L_)
+from wsss_analysis_b200.pipeline import BatchPipeline, pinned_empty   # async-host upload stream, sub-batches
+sz = [(32, 24)] * 5; n_ = 5 * 32 * 24
+U_ = pinned_empty(n_ * 4); U_[:] = np.concatenate([S.random_unary(4, 32 * 24, i).ravel() for i in range(5)])
+I_ = pinned_empty(n_ * 3, np.uint8); I_[:] = np.concatenate([S.natural_image(24, 32, i).ravel() for i in range(5)])
+with BatchPipeline(n_slots=2, chunk_images=2) as pipe:
+    pipe.result(pipe.submit(sz, 4, U_, I_, {"g_sxy": 3, "g_compat": 3, "bi_sxy": 40, "bi_srgb": 13, "bi_compat": 10, "iterations": 2}, out=pinned_empty(n_ * 4)))
 probs = np.stack([S.blob_probs(6, 24, 32, seed=i, n_active=3) for i in range(2)])
 wsss.dcrf_process(probs, np.stack([S.histo_image(24, 32, i) for i in range(2)]), (1.5, 3, 40, 13, 10, 3.0))
 wsss.crf_inference_label(S.natural_image(24, 32, 0).astype(np.float32), S.gt_map(24, 32, 4, 0, ignore=0), "voc12", n_labels=4)
