@@ -187,14 +187,16 @@ class ClockSampler(object):
 def algorithmic_bytes(cls, d, N, L, M, n_terms_info=None):
     """Algorithmic bytes of ONE launch (DESIGN.md section 'Roofline accounting'); float32 values,
     int32 ids, L real labels (padding lanes are not counted)."""
-    if cls == "splat":   # Q read + norm + (pixel id, weight) per entry + row starts + lattice write
-        return 4 * L * N + 4 * N + 8 * (d + 1) * N + 4 * M + 4 * L * M
+    # (the pre- / post-normalisation vectors are folded into the packed entry weights at build time,
+    # so no iteration kernel reads them and they are not counted)
+    if cls == "splat":   # Q read + (pixel id, weight) per entry + row starts + lattice write
+        return 4 * L * N + 8 * (d + 1) * N + 4 * M + 4 * L * M
     if cls == "blur":    # lattice read + write + two neighbour ids
         return 8 * L * M + 8 * M
-    if cls == "slice":   # unary read + Q write + per term: (offset, weight) per entry + lattice read + norm
+    if cls == "slice":   # unary read + Q write + per term: (vertex id, weight) per entry + lattice read
         b = 8 * L * N
         for (dk, Mk) in n_terms_info:
-            b += 8 * (dk + 1) * N + 4 * L * Mk + 4 * N
+            b += 8 * (dk + 1) * N + 4 * L * Mk
         return b
     raise KeyError(cls)
 

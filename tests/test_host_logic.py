@@ -129,9 +129,9 @@ def test_bench_algorithmic_bytes_formula():
     per_iter = (bench.algorithmic_bytes("splat", 2, N, L, Mg) + bench.algorithmic_bytes("splat", 5, N, L, Mb)
                 + 3 * bench.algorithmic_bytes("blur", 2, N, L, Mg) + 6 * bench.algorithmic_bytes("blur", 5, N, L, Mb)
                 + bench.algorithmic_bytes("slice", None, N, L, None, [(2, Mg), (5, Mb)]))
-    # SURVEY.md section 8d formula + one extra Q read (two splat launches) + norms and row starts
+    # SURVEY.md section 8d formula + one extra Q read (two splat launches) + the CSR row starts
     survey = 12 * L * N + sum(16 * (d + 1) * N + 8 * L * M + (d + 1) * (8 * L * M + 8 * M) for d, M in ((2, Mg), (5, Mb)))
-    extra = 4 * L * N + 4 * 4 * N + 4 * (Mg + Mb)
+    extra = 4 * L * N + 4 * (Mg + Mb)
     assert per_iter == survey + extra
 
 
