@@ -141,3 +141,22 @@ def test_wrapper_batches_are_chunked_below_the_int32_entry_limit(monkeypatch):
     assert wsss._chunks(range(5), [10] * 5) == [[0, 1], [2, 3], [4]]
     assert wsss._chunks([0, 2, 4], [30, 1, 2, 3, 40]) == [[0], [2], [4]]  # an over-size image runs alone
     assert wsss._chunks([], []) == []
+
+
+def test_pipeline_sub_batch_views():
+    """BatchPipeline._cut: images [lo, hi) of a flat concatenation or of a per-image list (the views
+    handed to the sub-batch handles; no GPU involved)."""
+    from wsss_analysis_b200.pipeline import BatchPipeline
+
+    sizes = [(4, 3), (2, 5), (6, 1)]
+    starts = np.concatenate([[0], np.cumsum([w * h for w, h in sizes])])
+    L = 3
+    flat = np.arange(int(starts[-1]) * L, dtype=np.float32)
+    got = BatchPipeline._cut(flat, 1, 3, starts, L)
+    assert got.base is flat or got.base is flat.base or np.shares_memory(got, flat)
+    assert got[0] == 12 * L and got.size == (10 + 6) * L
+    lst = ["a", "b", "c"]
+    assert BatchPipeline._cut(lst, 0, 2, starts, L) == ["a", "b"]
+    assert BatchPipeline._cut(None, 0, 2, starts, L) is None
+    rgb = np.zeros(int(starts[-1]) * 3, np.uint8)
+    assert BatchPipeline._cut(rgb, 2, 3, starts, 3).size == 6 * 3

@@ -22,6 +22,6 @@ for cls, cid in (("splat", 0), ("blur", 1), ("slice", 2)):
     for tag in ((2, 5) if cls != "slice" else (2,)):
         ms, n = crf.profile_read(cid, tag)
         if n: print("%s tag=%d: %d launches avg %.1f us total %.2f ms" % (cls, tag, n, ms / n * 1e3, ms)); tot += ms
-print("SB=%s B=%d iteration kernels total %.2f ms per 10 iters" % (os.environ.get("DCRF_SPLAT_SB", "4"), B, tot))
+print("B=%d iteration kernels total %.2f ms per 10 iters" % (B, tot))
 import hashlib
 print("Q sha1", hashlib.sha1(Q.cpu().numpy().tobytes()).hexdigest()[:16])
