@@ -96,13 +96,16 @@ void dcrf_destroy(dcrf_t *h);
 /* Options.  DCRF_OPT_EXACT_ARITHMETIC = 1 makes the per-iteration kernels use the specification's
  * float association literally (separately rounded multiply/add, libm-accurate exp and division, no
  * folding of the normalisation into the splat weights): lattice values then match a sequential CPU
- * evaluation bit for bit, at roughly half the speed.  Default 0 (FMA / ex2.approx fast path; both
- * modes are run-to-run deterministic and within the 1e-4 tolerance on Q). */
+ * evaluation bit for bit, at roughly half the speed.  Default 0 (fast path: FMA, normalisation
+ * folded into the packed entry weights, one reciprocal per softmax; expf stays the accurate one).
+ * Both modes are run-to-run deterministic and within the 1e-4 tolerance on Q. */
 /* DCRF_OPT_ASYNC_HOST = 1: calls that read or write caller HOST buffers only enqueue their copies on
  * the handle's stream and return; the caller keeps the buffers alive and untouched until
  * dcrf_synchronize().  Lets one host thread keep two handles (two streams) in flight so that the
  * PCIe copies of one batch overlap the kernels of the other (wsss_analysis_b200/pipeline.py).
- * Host buffers should be page-locked, otherwise the copies are not asynchronous. */
+ * Host buffers should be page-locked, otherwise the copies are not asynchronous.  In this mode
+ * dcrf_set_unary runs its upload and layout change on a separate per-thread stream, so the lattice
+ * builds enqueued next overlap the upload; the handle's stream waits for it before the unary is read. */
 enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2 };
 int dcrf_set_option(dcrf_t *h, int option, int value);
 /* block the calling thread until everything enqueued on the handle's stream has finished */
