@@ -76,3 +76,26 @@ def test_shim_resolves_reference_imports():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "shim"))
     out = subprocess.check_output([sys.executable, "-c", code], env=env, cwd="/tmp").decode()
     assert out.split() == ["wsss_analysis_b200.densecrf", "1", "3"]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++ in the signatures) and a C program
+    that references every declared entry point links against the shared library with gcc alone."""
+    import re
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "dcrf_b200.h")
+    names = sorted(set(re.findall(r"\b(dcrf_[a-z0-9_]+)\s*\(", open(hdr).read())))
+    src = tmp_path / "link_all.c"
+    body = "\n".join("    p[%d] = (fn)%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "dcrf_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\n'
+                   'int main(void) {\n    fn p[%d];\n%s\n'
+                   '    printf("%%d %%s\\n", (int)(sizeof p / sizeof p[0]), dcrf_version());\n    return p[0] == 0;\n}\n'
+                   % (len(names), body))
+    exe = tmp_path / "link_all"
+    libdir = os.path.join(ROOT, "wsss_analysis_b200", "csrc")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-ldcrf_b200", "-Wl,-rpath," + libdir],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and out[1].startswith("dcrf_b200")
