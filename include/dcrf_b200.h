@@ -93,12 +93,20 @@ int dcrf_create_batch(int n_images, const int *w, const int *h, int n_labels, in
 
 void dcrf_destroy(dcrf_t *h);
 
-/* Options.  DCRF_OPT_EXACT_ARITHMETIC = 1 makes the per-iteration kernels use the specification's
- * float association literally (separately rounded multiply/add, libm-accurate exp and division, no
- * folding of the normalisation into the splat weights): lattice values then match a sequential CPU
- * evaluation bit for bit, at roughly half the speed.  Default 0 (fast path: FMA, normalisation
- * folded into the packed entry weights, one reciprocal per softmax; expf stays the accurate one).
- * Both modes are run-to-run deterministic and within the 1e-4 tolerance on Q. */
+/* Options.  DCRF_OPT_EXACT_ARITHMETIC selects the float arithmetic of the per-iteration kernels:
+ *   DCRF_ARITH_REFERENCE (1, default): the association of the sequential CPU evaluation [EXT],
+ *     operation for operation -- separately rounded multiply / add in splat and slice, normalisation
+ *     applied as its own rounded product, expf as the host libm (glibc) evaluates it, softmax sum in
+ *     label order, IEEE division.  Marginals are bit-identical to such an evaluation, with one
+ *     exception: splat rows with more than 256 entries (flat image regions) are summed as 256
+ *     sequential terms + a fixed tree over the tail.
+ *   DCRF_ARITH_STRICT (2): as 1 without that exception (a lattice vertex shared by thousands of
+ *     pixels is then summed by one lane group: slow on flat images).
+ *   DCRF_ARITH_FMA (0): fused multiply-add, normalisation folded into the packed entry weights, one
+ *     reciprocal per softmax, CUDA expf.  Differs from the others by float rounding only.
+ * All modes are run-to-run deterministic.  The environment variable DCRF_ARITHMETIC = fma | reference
+ * | strict overrides the default of handles created afterwards. */
+enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2 };
 /* DCRF_OPT_ASYNC_HOST = 1: calls that read or write caller HOST buffers only enqueue their copies on
  * the handle's stream and return; the caller keeps the buffers alive and untouched until
  * dcrf_synchronize().  Lets one host thread keep two handles (two streams) in flight so that the
@@ -190,6 +198,9 @@ int dcrf_lattice_info(dcrf_t *h, int kernel, int *d_out, int64_t *M_out, int64_t
  *   neighbours (d+1, M_b, 2) int32 with -1 = absent; norm (N_b) float32. */
 int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t *offsets,
                         float *bary, int32_t *neighbours, float *norm);
+/* y[i] = expf(x[i]) as the reference-arithmetic softmax evaluates it (restatement of glibc's
+ * double-precision expf for x <= 0); host buffers.  Test hook. */
+int dcrf_expf_ref(const float *x, float *y, int64_t n, int device);
 /* one application of pairwise kernel `kernel`'s lattice filter (splat, blur, slice; no norm, no
  * compat) to host values (L, N) -> (L, N); batch-of-one only.  Test hook. */
 int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int value_size);

@@ -24,8 +24,8 @@ _POTTS, _DIAGONAL, _MATRIX = 0, 1, 2
 
 def build(force=False):
     """Compile the oracle with gcc (building the checker is not using it)."""
-    src = os.path.join(_HERE, "densecrf_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("densecrf_oracle.c", "expf_ref.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_dcrf.so"],
                               stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -71,6 +71,11 @@ def lib():
         L.orc_crf_kl_divergence.restype = C.c_double
         L.orc_crf_kl_divergence.argtypes = [vp, vp]
         L.orc_bruteforce_gaussian.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int]
+        L.orc_expf_ref.restype = C.c_float
+        L.orc_expf_ref.argtypes = [C.c_float]
+        L.orc_expf_host.argtypes = [vp, vp, C.c_int64]
+        L.orc_expf_ref_check.restype = C.c_int64
+        L.orc_expf_ref_check.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.orc_confusion_accumulate.restype = C.c_int64
         L.orc_confusion_accumulate.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
         _lib = L
@@ -251,3 +256,19 @@ def confusion(gt, pred, C_):
     conf = np.zeros((C_ + 1, C_), np.int64)
     lib().orc_confusion_accumulate(_ptr(gt), _ptr(pred), gt.size, C_, _ptr(conf))
     return conf
+
+
+def expf_host(x):
+    """libm expf element-wise (float32) -- the routine the oracle's softmax calls."""
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.empty_like(x)
+    lib().orc_expf_host(_ptr(x), _ptr(y), x.size)
+    return y
+
+
+def expf_ref_mismatches(u_lo=0x80000000, u_hi=0xC2D00000, stride=1):
+    """Number of float bit patterns in [u_lo, u_hi] (step `stride`) where the restated glibc expf
+    (expf_ref.c) differs from the host libm, and the first such pattern."""
+    first = C.c_uint32(0)
+    n = lib().orc_expf_ref_check(u_lo, u_hi, stride, C.byref(first))
+    return int(n), int(first.value)

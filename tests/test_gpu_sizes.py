@@ -60,7 +60,8 @@ def test_adp_1088_full_size_vs_oracle():
 
 
 def test_adp_1088_morph_properties():
-    """1088x1088 with the 29-label ADP-morph set: too slow for the oracle, checked by properties."""
+    """1088x1088 with the 29-label ADP-morph set: size-independent properties (the comparison with
+    the oracle at this size is tests/test_gpu_reference_arith.py::test_adp_1088_morph_29_labels_vs_oracle)."""
     from wsss_analysis_b200 import densecrf as G
     from wsss_analysis_b200 import synthetic as S
 
@@ -121,12 +122,11 @@ def test_deepglobe_612_vs_oracle():
     Qo, Qg, Qx = o.inference(10), g.inference(10), gx.inference(10)
     assert o.lattice(1).M == g.lattice_export(1)["M"]
     # Pure-noise unaries + srgb = 5 + 10 iterations make the mean-field map expansive at a handful
-    # of bistable pixels: 1-ulp differences grow ~2.5x per iteration ("Numerical
-    # note").  The exact-arithmetic mode stays within 1e-4 everywhere; the default fast path stays
-    # within 1e-4 on >= 99.99 % of the pixels and within 1e-3 on all of them.
+    # of bistable pixels (rounding differences grow ~2.5x per iteration).  The
+    # default arithmetic follows the oracle operation for operation, so BASELINE's 1e-4 holds with
+    # room to spare (tests/test_gpu_reference_arith.py asserts bit identity and covers the FMA mode).
     assert np.abs(Qo - Qx).max() <= 1e-4
-    dmax = np.abs(Qo - Qg).max(0)
-    assert (dmax <= 1e-4).mean() >= 0.9999 and dmax.max() <= 1e-3
+    assert np.abs(Qo - Qg).max() <= 1e-4
     assert (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999
 
 

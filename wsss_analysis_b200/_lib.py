@@ -48,6 +48,7 @@ SIGNATURES = {
     "dcrf_lattice_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i64), _vp]),
     "dcrf_lattice_export": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "dcrf_lattice_filter": (_i, [_vp, _i, _vp, _vp, _i]),
+    "dcrf_expf_ref": (_i, [_vp, _vp, _i64, _i]),
     "dcrf_profile_enable": (_i, [_vp, _i]),
     "dcrf_profile_read": (_i, [_vp, _i, _i, C.POINTER(C.c_double), C.POINTER(_i64), _i]),
     "dcrf_resize_nearest_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp]),

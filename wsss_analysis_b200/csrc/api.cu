@@ -2,6 +2,7 @@
 // mean-field loop.  One handle = a batch of independent images sharing L; all kernels run over the
 // concatenated pixel / vertex arrays of the batch on the handle's stream.
 #include <math.h>
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -128,7 +129,7 @@ struct dcrf_handle {
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
     bool unary_set = false, q_valid = false;
-    bool exact = false;       // DCRF_OPT_EXACT_ARITHMETIC
+    int arith = kArithFma;    // DCRF_OPT_EXACT_ARITHMETIC: kArithFma / kArithRef / kArithStrict
     bool async_host = false;  // DCRF_OPT_ASYNC_HOST
     std::vector<std::unique_ptr<Pairwise>> pw;
     Profiler prof;
@@ -192,6 +193,17 @@ void join_upload(dcrf_handle *h) {
 
 int64_t total_ln(const dcrf_handle *h) { return h->geom.Ntot * (int64_t)h->L; }
 
+// default arithmetic of new handles: reference association unless DCRF_ARITHMETIC says otherwise
+int default_arith() {
+    const char *e = getenv("DCRF_ARITHMETIC");
+    if (!e || !*e) return kArithRef;
+    if (!strcmp(e, "fma") || !strcmp(e, "0")) return kArithFma;
+    if (!strcmp(e, "strict") || !strcmp(e, "2")) return kArithStrict;
+    DCRF_REQUIRE(!strcmp(e, "reference") || !strcmp(e, "1"), DCRF_EINVAL,
+                 "DCRF_ARITHMETIC must be fma, reference or strict");
+    return kArithRef;
+}
+
 void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, int device, void *stream,
                    dcrf_t **out) {
     DCRF_REQUIRE(out != nullptr, DCRF_EINVAL, "out handle pointer is NULL");
@@ -219,6 +231,7 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     h->L = L;
     h->Lp = ((L + 3) / 4) * 4;
     h->has_geom = has_geom;
+    h->arith = default_arith();
     BatchGeom &g = h->geom;
     g.B = B;
     g.w.resize(B);
@@ -269,7 +282,7 @@ const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int
                                bool seq, float *bufA, float *bufB, bool fast = false,
                                cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
-    if (fast) launch_splat_fast(p.lat, in, bufA, Lp, st);  // pre-norm folded into the weights
+    if (fast) launch_splat_fast(p.lat, in, bufA, Lp, st);  // packed tables (pre-norm inside them)
     else launch_splat(p.lat, in, pre_norm ? p.norm.p : nullptr, bufA, Lp, st);
     float *cur = bufA, *nxt = bufB;
     for (int j = 0; j <= p.lat.d; j++) {
@@ -281,6 +294,15 @@ const float *filter_to_lattice(dcrf_handle *h, Pairwise &p, const float *in, int
 
 bool pre_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_BEFORE; }
 bool post_norm(int ntype) { return ntype == DCRF_NORMALIZE_SYMMETRIC || ntype == DCRF_NORMALIZE_AFTER; }
+
+// packed entry tables of the handle's arithmetic mode (norm: the kernel's [Ntot] vector or nullptr)
+void pack_tables(dcrf_handle *h, Lattice &lat, int ntype, const float *norm, cudaStream_t s) {
+    if (h->arith == kArithFma)
+        launch_pack_fast_tables(lat, pre_norm(ntype) ? norm : nullptr, post_norm(ntype) ? norm : nullptr, s);
+    else
+        launch_pack_ref_tables(lat, pre_norm(ntype) ? norm : nullptr, h->arith == kArithStrict ? INT_MAX : 0, s);
+}
+int wanted_tables(const dcrf_handle *h) { return h->arith == kArithFma ? kTablesFma : kTablesRef; }
 
 void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const float *compat, int ktype,
                   int ntype) {
@@ -341,7 +363,7 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         norm.alloc(bg.Ntot, s);
         launch_kernel_norm(lat, bg.Ntot, ntype, norm.p, s);
     }
-    launch_pack_fast_tables(lat, pre_norm(ntype) ? norm.p : nullptr, post_norm(ntype) ? norm.p : nullptr, s);
+    pack_tables(h, lat, ntype, norm.p, s);
     if (uniform) {
         if (norm.p) p->norm.alloc(Ntot, s);
         launch_replicate_lattice(single, norm.p, h->geom.B, bg.Ntot, p->lat, p->norm.p, s);
@@ -374,7 +396,7 @@ void start_inference(dcrf_handle *h) {
     memset(&a, 0, sizeof(a));
     a.n_terms = 0;
     a.seq = h->L <= 2 ? 1 : 0;
-    a.fast = (!h->exact && h->L > 2) ? 1 : 0;
+    a.fast = h->L <= 2 ? kSliceLiteral : (h->arith == kArithFma ? kSliceFma : kSliceRef);
     launch_slice_softmax(a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, h->stream);
     h->q_valid = true;
 }
@@ -382,12 +404,20 @@ void start_inference(dcrf_handle *h) {
 void step_inference(dcrf_handle *h) {
     DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "stepInference before startInference");
     const bool seq = h->L <= 2;
-    const bool fast = !h->exact && !seq && h->geom.Ntot * (int64_t)(h->Lp / 4) < ((int64_t)1 << 31);
+    // packed-table kernels index rows with 32 bits: (largest row index) * (float4 per row) < 2^32
+    int64_t max_rows = h->geom.Ntot;
+    for (auto &p : h->pw) max_rows = std::max<int64_t>(max_rows, p->lat.M);
+    const bool fast = !seq && max_rows * (int64_t)(h->Lp / 4) < ((int64_t)1 << 32) &&
+                      h->geom.Ntot * (int64_t)(h->Lp / 4) < ((int64_t)1 << 31);
     SliceArgs a;
     memset(&a, 0, sizeof(a));
     a.seq = seq ? 1 : 0;
-    a.fast = fast ? 1 : 0;
+    a.fast = !fast ? kSliceLiteral : (h->arith == kArithFma ? kSliceFma : kSliceRef);
+    a.max_rows = max_rows;
     const int n = (int)h->pw.size();
+    if (fast)  // the arithmetic option was changed after the kernel was added: repack its tables
+        for (auto &p : h->pw)
+            if (p->lat.table_mode != wanted_tables(h)) pack_tables(h, p->lat, p->ntype, p->norm.p, h->stream);
     // per-kernel profiling wants serialised kernels; otherwise fork the first n-1 terms
     const bool overlap = n >= 2 && !h->prof.on;
     if (overlap) {
@@ -536,8 +566,12 @@ int dcrf_set_option(dcrf_t *h, int option, int value) {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
         DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC || option == DCRF_OPT_ASYNC_HOST, DCRF_EINVAL,
                      "unknown option");
-        if (option == DCRF_OPT_EXACT_ARITHMETIC) h->exact = value != 0;
-        else h->async_host = value != 0;
+        if (option == DCRF_OPT_EXACT_ARITHMETIC) {
+            DCRF_REQUIRE(value >= 0 && value <= 2, DCRF_EINVAL, "arithmetic mode must be 0, 1 or 2");
+            h->arith = value;
+        } else {
+            h->async_host = value != 0;
+        }
     });
 }
 
@@ -936,6 +970,27 @@ int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t
                 neighbours[2 * i + 0] = nb[i].x >= 0 ? nb[i].x - (int32_t)v0 : -1;
                 neighbours[2 * i + 1] = nb[i].y >= 0 ? nb[i].y - (int32_t)v0 : -1;
             }
+    });
+}
+
+int dcrf_expf_ref(const float *x, float *y, int64_t n, int device) {
+    return guarded([&] {
+        DCRF_REQUIRE((x && y) || n == 0, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(n >= 0, DCRF_EINVAL, "n must be >= 0");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw Error{DCRF_ECUDA, "no CUDA device: dcrf_b200 has no CPU fallback"};
+        if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
+        DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
+        DeviceGuard guard(device);
+        cudaStream_t s = thread_main_stream(device);
+        DevBuf<float> dx, dy;
+        dx.alloc((size_t)n, s);
+        dy.alloc((size_t)n, s);
+        DCRF_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        launch_expf_ref(dx.p, dy.p, n, s);
+        DCRF_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(cudaStreamSynchronize(s));
     });
 }
 

@@ -160,6 +160,11 @@ struct Lattice {
     // packed tables of the fast path (one 64-bit load per entry instead of two 32-bit loads)
     DevBuf<int2> ent;              // [E] (vertex id, weight * post-norm[pixel] bits) of entry e
     DevBuf<int2> csr_ent;          // [E] (pixel, weight * pre-norm[pixel] bits) of each sorted entry
+    // reference-association tables (arithmetic identical to the sequential CPU evaluation):
+    // ent = (vertex id, bary * alpha), csr_ent4 = (pixel, weight, pre-norm[pixel] or 1, 0)
+    DevBuf<int4> csr_ent4;         // [E]
+    int table_mode = 0;            // kTables*: which of the packed tables are valid
+    int long_row_cap = 0;          // rows longer than this are cut (tail: splat_long_tail_kernel); INT_MAX = never
     DevBuf<int> row_counter;       // [1] dynamic row-chunk dispenser of the fast splat
     DevBuf<int32_t> long_rows;     // rows with more than kSplatLongRow entries (tail summed by a whole CTA)
     DevBuf<int> n_long;            // [1] their number (device side)
@@ -191,8 +196,18 @@ struct SliceArgs {
     SliceTerm term[kMaxPairwise];
     int n_terms;
     int seq;  // value_size <= 2 association (A.4)
-    int fast; // fused-multiply-add / fast-exp path allowed (handle not in exact-arithmetic mode)
+    int fast; // kSlice*: which family of kernels to use
+    int64_t max_rows; // largest lattice vertex count among the terms (32-bit row indexing guard)
 };
+// arithmetic modes of the per-iteration kernels (DCRF_OPT_EXACT_ARITHMETIC values)
+constexpr int kArithFma = 0;     // FMA accumulation, normalisation folded into the packed weights
+constexpr int kArithRef = 1;     // the specification's association on packed tables (bit-identical to the
+                                 // sequential CPU evaluation except for the tails of very long splat rows)
+constexpr int kArithStrict = 2;  // kArithRef without the long-row split
+constexpr int kTablesNone = 0, kTablesFma = 1, kTablesRef = 2;
+// SliceArgs::fast: literal per-entry kernels (value_size <= 2, diagonal / matrix compatibility), FMA
+// kernels on packed tables, reference-association kernels on packed tables
+constexpr int kSliceLiteral = 0, kSliceFma = 1, kSliceRef = 2;
 
 // values <- splat of (pre ? norm (.) Q : Q)       (A.4 splat, A.5 pre-scaling)
 void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, float *val, int Lp,
@@ -200,6 +215,8 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
 // fast path: packed tables; splat weights pre-multiplied by the pre-normalisation, slice weights by
 // the post-normalisation (the fast kernels never read the norm vector), FMA accumulation
 void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *norm_post, cudaStream_t s);
+// reference-association tables; long_row_cap as in Lattice
+void launch_pack_ref_tables(Lattice &lat, const float *norm_pre, int long_row_cap, cudaStream_t s);
 void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s);
 void launch_find_long_rows(Lattice &lat, cudaStream_t s);
 // out <- in + 0.5 (in[n1] + in[n2]) along axis j  (A.4 blur)
@@ -229,6 +246,8 @@ void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp
 // >= min_prob and renormalised over labels in NumPy's summation order, optionally log
 void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, float min_prob, int renorm,
                      int take_log, cudaStream_t s);
+// y = expf(x) as evaluated by the reference-association softmax (softmax_ref.cuh); test hook
+void launch_expf_ref(const float *x, float *y, int64_t n, cudaStream_t s);
 // deterministic double-precision KL terms
 void launch_kl(const float *Q, const float *unary, const float *const *pair_out, int n_pair,
                int64_t Ntot, int L, int Lp, double *out, cudaStream_t s);

@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "softmax_ref.cuh"
 
 namespace dcrf {
 
@@ -155,12 +156,42 @@ __global__ void __launch_bounds__(kThreads) pack_fast_tables_kernel(
     csr_ent[e] = make_int2(p, __float_as_int(w));
 }
 
+// Reference-association tables: nothing is folded that the sequential evaluation rounds separately.
+//   ent      = (vertex id, bary * alpha)            -- A.4 slice: wa = w * alpha; acc += wa * v
+//   csr_ent4 = (pixel, bary, pre-norm[pixel] | 1, 0) -- A.5 / A.4 splat: val += w * (norm * Q)
+// (multiplying by 1.0f is exact, so kernels without a pre-normalisation use the same code path)
+__global__ void __launch_bounds__(kThreads) pack_ref_tables_kernel(
+    const int32_t *__restrict__ offset, const float *__restrict__ bary, const int32_t *__restrict__ csr_pix,
+    const float *__restrict__ csr_w, const float *__restrict__ norm_pre, float alpha, int2 *__restrict__ ent,
+    int4 *__restrict__ csr_ent4, int64_t E) {
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    ent[e] = make_int2(offset[e], __float_as_int(__fmul_rn(bary[e], alpha)));
+    const int p = csr_pix[e];
+    const float n = norm_pre ? norm_pre[p] : 1.0f;
+    csr_ent4[e] = make_int4(p, __float_as_int(csr_w[e]), __float_as_int(n), 0);
+}
+
+// packed CSR entry of the splat: FMA tables (pixel, w * norm) or reference tables (pixel, w, norm, -)
+template <bool REF> struct CsrEnt { typedef int2 type; };
+template <> struct CsrEnt<true> { typedef int4 type; };
+__device__ __forceinline__ int2 zero_ent(int2) { return make_int2(0, 0); }
+__device__ __forceinline__ int4 zero_ent(int4) { return make_int4(0, 0, 0, 0); }
+
 __device__ __forceinline__ void fma4(float4 &acc, float w, const float4 q) {
     acc.x = fmaf(w, q.x, acc.x);
     acc.y = fmaf(w, q.y, acc.y);
     acc.z = fmaf(w, q.z, acc.z);
     acc.w = fmaf(w, q.w, acc.w);
 }
+
+template <bool REF>
+__device__ __forceinline__ void splat_acc(float4 &acc, float w, float n, const float4 q) {
+    if (REF) mul_add(acc, w, scale4(q, n));  // val += w * (norm * Q), every product rounded (A.4, A.5)
+    else fma4(acc, w, q);
+}
+__device__ __forceinline__ float ent_norm(const int2) { return 1.0f; }
+__device__ __forceinline__ float ent_norm(const int4 e) { return __int_as_float(e.z); }
 
 // Work distribution: rows differ wildly in length (bilateral lattice: median 6, p99 46, max > 150
 // entries), so rows are handed out dynamically.  A warp claims chunks of 32 consecutive rows with
@@ -174,13 +205,18 @@ constexpr int kSplatChunk = 32;
 // thousands of entries each) are cut: one lane group sums the first kSplatLongRow entries here, a
 // whole CTA per row sums the tail in splat_long_tail_kernel.  Natural images have no such row.
 constexpr int kSplatLongRow = 256;
+#ifndef DCRF_TUNE_SPLAT_REF_MINB
+#define DCRF_TUNE_SPLAT_REF_MINB 0  // 0: same __launch_bounds__ minimum as the FMA kernel of that G
+#endif
+constexpr int kSplatRefMinBlocks = DCRF_TUNE_SPLAT_REF_MINB;
 
-template <int G, int SB>
+template <int G, int SB, bool REF>
 __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
-                                                              const int2 *__restrict__ csr_ent,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                               const float4 *__restrict__ Q4,
                                                               float4 *__restrict__ val4, int M, int g_rt,
-                                                              int *__restrict__ row_counter) {
+                                                              int *__restrict__ row_counter, int long_cap) {
+    typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     const int g = G ? G : g_rt;
     const int lane = threadIdx.x & 31;
@@ -195,9 +231,9 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
     bool exhausted = false;
     // per-group state: current row v with entries [s, s1); e_cur = its current batch, already loaded
     int v = -1, s = 0, s1 = 0, cnt_cur = 0;
-    int2 e_cur[SB];
+    Ent e_cur[SB];
 #pragma unroll
-    for (int i = 0; i < SB; i++) e_cur[i] = make_int2(0, 0);
+    for (int i = 0; i < SB; i++) e_cur[i] = zero_ent(Ent());
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     // Software pipeline: in every trip the row gathers of batch k and the entry loads of batch k+1
     // (possibly of the group's NEXT row, claimed one trip ahead) are in flight together.
@@ -241,18 +277,18 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
             if (need) {
                 nv = take ? row : -1;
                 ns = b0;
-                ns1 = min(b1, b0 + kSplatLongRow);  // the rest of a very long row: splat_long_tail_kernel
+                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;  // the rest of a very long row: splat_long_tail_kernel
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
         // 3. entry loads of the next batch
         const int ncnt = nv >= 0 ? min(SB, ns1 - ns) : 0;
-        int2 e_next[SB];
+        Ent e_next[SB];
 #pragma unroll
-        for (int i = 0; i < SB; i++) e_next[i] = (i < ncnt) ? __ldg(csr_ent + ns + i) : make_int2(0, 0);
+        for (int i = 0; i < SB; i++) e_next[i] = (i < ncnt) ? __ldg(csr_ent + ns + i) : zero_ent(Ent());
         // 4. consume the current batch (padded slots add 0 * 0)
 #pragma unroll
-        for (int i = 0; i < SB; i++) fma4(acc, __int_as_float(e_cur[i].y), q[i]);
+        for (int i = 0; i < SB; i++) splat_acc<REF>(acc, __int_as_float(e_cur[i].y), ent_norm(e_cur[i]), q[i]);
         if (v >= 0 && row_ends) {
             val4[(unsigned)v * g + c] = acc;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -274,12 +310,13 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
 // group loads entry c of the batch (one request per G entries) and the (pixel, weight) pairs are
 // broadcast inside the group with shuffles.  A trip handles NB * G entries.  Summation order and
 // arithmetic are unchanged, so the result is bit-identical to splat_fast_kernel.
-template <int G, int NB, int MINB>
+template <int G, int NB, int MINB, bool REF>
 __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
-                                                              const int2 *__restrict__ csr_ent,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                               const float4 *__restrict__ Q4,
                                                               float4 *__restrict__ val4, int M,
-                                                              int *__restrict__ row_counter) {
+                                                              int *__restrict__ row_counter, int long_cap) {
+    typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int SB = G * NB;
     constexpr int gpw = 32 / G;
@@ -293,9 +330,9 @@ __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_
     int bounds = 0, bound_last = 0;
     bool exhausted = false;
     int v = -1, s = 0, s1 = 0, cnt_cur = 0;
-    int2 e_cur[NB];
+    Ent e_cur[NB];
 #pragma unroll
-    for (int b = 0; b < NB; b++) e_cur[b] = make_int2(0, 0);
+    for (int b = 0; b < NB; b++) e_cur[b] = zero_ent(Ent());
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (;;) {
         // 1. broadcast the batch's entries inside the group, request the row gathers
@@ -338,22 +375,25 @@ __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_
             if (need) {
                 nv = take ? row : -1;
                 ns = b0;
-                ns1 = min(b1, b0 + kSplatLongRow);
+                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
         // 3. cooperative entry loads of the next batch: lane c takes entries c, c + G, ...
         const int ncnt = nv >= 0 ? min(SB, ns1 - ns) : 0;
-        int2 e_next[NB];
+        Ent e_next[NB];
 #pragma unroll
         for (int b = 0; b < NB; b++)
-            e_next[b] = (b * G + c < ncnt) ? __ldg(csr_ent + ns + b * G + c) : make_int2(0, 0);
+            e_next[b] = (b * G + c < ncnt) ? __ldg(csr_ent + ns + b * G + c) : zero_ent(Ent());
         // 4. consume (padded slots add 0 * 0)
 #pragma unroll
         for (int b = 0; b < NB; b++)
 #pragma unroll
-            for (int i = 0; i < G; i++)
-                fma4(acc, __int_as_float(__shfl_sync(FULL, e_cur[b].y, (gbase + i) & 31)), q[b * G + i]);
+            for (int i = 0; i < G; i++) {
+                const float w = __int_as_float(__shfl_sync(FULL, e_cur[b].y, (gbase + i) & 31));
+                const float n = REF ? __shfl_sync(FULL, ent_norm(e_cur[b]), (gbase + i) & 31) : 1.0f;
+                splat_acc<REF>(acc, w, n, q[b * G + i]);
+            }
         if (v >= 0 && row_ends) {
             val4[(unsigned)v * G + c] = acc;
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -368,22 +408,23 @@ __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_
     }
 }
 
-// rows with more than kSplatLongRow entries (found at build time, any order: rows are independent)
+// rows with more than long_cap entries (found at build time, any order: rows are independent)
 __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t *__restrict__ csr_start, int64_t M,
                                                                   int32_t *__restrict__ long_rows,
-                                                                  int *__restrict__ n_long) {
+                                                                  int *__restrict__ n_long, int long_cap) {
     const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (v >= M) return;
-    if (csr_start[v + 1] - csr_start[v] > kSplatLongRow) long_rows[atomicAdd(n_long, 1)] = (int32_t)v;
+    if (csr_start[v + 1] - csr_start[v] > long_cap) long_rows[atomicAdd(n_long, 1)] = (int32_t)v;
 }
 
-// val[v] += sum of the entries beyond the first kSplatLongRow of each long row v.  One CTA per row:
+// val[v] += sum of the entries beyond the first long_cap of each long row v.  One CTA per row:
 // lane group k sums entries k, k + n_groups, ... in order, then the groups are combined by a fixed
-// binary tree in shared memory => deterministic.
-template <int G>
+// binary tree in shared memory => deterministic (but not the sequential order of the specification).
+template <int G, bool REF>
 __global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
-    const int32_t *__restrict__ csr_start, const int2 *__restrict__ csr_ent, const float4 *__restrict__ Q4,
-    float4 *__restrict__ val4, const int32_t *__restrict__ long_rows, const int *__restrict__ n_long, int g_rt) {
+    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
+    const int *__restrict__ n_long, int g_rt, int long_cap) {
     extern __shared__ float4 part[];  // [n_groups][g]
     const int g = G ? G : g_rt;
     const int n_groups = kThreads / g;
@@ -392,12 +433,12 @@ __global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
     const int n = *n_long;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int v = long_rows[i];
-        const int s0 = csr_start[v] + kSplatLongRow, s1 = csr_start[v + 1];
+        const int s0 = csr_start[v] + long_cap, s1 = csr_start[v + 1];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (on)
             for (int s = s0 + k; s < s1; s += n_groups) {
-                const int2 e = __ldg(csr_ent + s);
-                fma4(acc, __int_as_float(e.y), __ldg(Q4 + ((unsigned)e.x * g + c)));
+                const typename CsrEnt<REF>::type e = __ldg(csr_ent + s);
+                splat_acc<REF>(acc, __int_as_float(e.y), ent_norm(e), __ldg(Q4 + ((unsigned)e.x * g + c)));
             }
         if (on) part[k * g + c] = acc;
         __syncthreads();
@@ -627,34 +668,10 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_kernel(const SliceArgs
         t.z = __fsub_rn(t.z, y.z);
         t.w = __fsub_rn(t.w, y.w);
     }
-    // softmax over the L valid labels of the row (max-subtracted)
-    const int l0 = c * 4;
-    const float NEG = -INFINITY;
-    float m = NEG;
-    if (l0 + 0 < L) m = fmaxf(m, t.x);
-    if (l0 + 1 < L) m = fmaxf(m, t.y);
-    if (l0 + 2 < L) m = fmaxf(m, t.z);
-    if (l0 + 3 < L) m = fmaxf(m, t.w);
-    const int lane = threadIdx.x & 31;
-    const int gbase = lane - c;
-    float mx = NEG;
-    for (int i = 0; i < g; i++) mx = fmaxf(mx, __shfl_sync(0xffffffffu, m, (gbase + i) & 31));
-    float4 e;
-    e.x = (l0 + 0 < L) ? expf(__fsub_rn(t.x, mx)) : 0.f;
-    e.y = (l0 + 1 < L) ? expf(__fsub_rn(t.y, mx)) : 0.f;
-    e.z = (l0 + 2 < L) ? expf(__fsub_rn(t.z, mx)) : 0.f;
-    e.w = (l0 + 3 < L) ? expf(__fsub_rn(t.w, mx)) : 0.f;
-    const float ls = __fadd_rn(__fadd_rn(__fadd_rn(e.x, e.y), e.z), e.w);
-    float sum = 0.f;
-    for (int i = 0; i < g; i++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, ls, (gbase + i) & 31));
-    if (act) {
-        float4 q;
-        q.x = __fdiv_rn(e.x, sum);
-        q.y = __fdiv_rn(e.y, sum);
-        q.z = __fdiv_rn(e.z, sum);
-        q.w = __fdiv_rn(e.w, sum);
-        st4(Q + (p * g + c) * 4, q);
-    }
+    // softmax over the L valid labels of the row: libm-identical expf, sum in label order (A.7)
+    const ExpfRef ex;
+    const float4 q = softmax_ref_row<G>(t, L, c, g, (int)(threadIdx.x & 31) - c, ex);
+    if (act) st4(Q + (p * g + c) * 4, q);
 }
 
 // Fast fused slice for the reference configuration: term 0 with d = DA, term 1 with d = DB, both
@@ -859,6 +876,123 @@ __global__ void __launch_bounds__(kThreads) softmax_unary_fast_kernel(const floa
         const float inv = 1.0f / sum;
         Q4[p * g + c] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-association fused slice (kSliceRef): the packed-table / cooperative-load structure of the
+// FMA kernels above with the arithmetic of the sequential CPU evaluation, operation for operation:
+//   x_k = sum_r (bary_r * alpha_k) * v_r   separately rounded products and sums, r ascending  (A.4)
+//   y_k = (-w_k) * (x_k * norm_k[p])                                                          (A.5, A.6)
+//   t   = ((-U) - y_0) - y_1 ...;   Q = softmax_ref_row(t)                                    (A.7)
+// so Q is bit-identical to oracle/densecrf_oracle.c whenever the lattice values are.
+// ---------------------------------------------------------------------------------------------
+template <int D, int G>
+__device__ __forceinline__ float4 slice_ref_row_coop(const int2 *__restrict__ ent, const float4 *__restrict__ val4,
+                                                     unsigned p, unsigned c, int gbase) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NL = (D + G) / G;
+    int2 e[NL];
+    const int2 *ep = ent + (size_t)p * (D + 1);
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+        const int idx = (int)c + j * G;
+        e[j] = idx <= D ? __ldg(ep + idx) : make_int2(0, 0);
+    }
+    float4 v[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        const unsigned vx = (unsigned)__shfl_sync(FULL, e[r / G].x, (gbase + r % G) & 31);
+        v[r] = __ldg(val4 + (vx * G + c));
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r <= D; r++)
+        mul_add(acc, __int_as_float(__shfl_sync(FULL, e[r / G].y, (gbase + r % G) & 31)), v[r]);
+    return acc;
+}
+
+__device__ __forceinline__ float4 slice_ref_row_rt(const int2 *__restrict__ ent, const float4 *__restrict__ val4,
+                                                   unsigned p, int d, unsigned g, unsigned c) {
+    const int2 *ep = ent + (size_t)p * (d + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 <= d; r0 += 4) {  // 4 gathers in flight
+        int2 e[4];
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) e[i] = r0 + i <= d ? __ldg(ep + r0 + i) : make_int2(0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            v[i] = r0 + i <= d ? __ldg(val4 + ((unsigned)e[i].x * g + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (r0 + i <= d) mul_add(acc, __int_as_float(e[i].y), v[i]);
+    }
+    return acc;
+}
+
+// t -= (-w) * (x * n)
+__device__ __forceinline__ void sub_potts(float4 &t, const float4 x, float n, float w) {
+    const float nw = -w;
+    t.x = __fsub_rn(t.x, __fmul_rn(nw, __fmul_rn(x.x, n)));
+    t.y = __fsub_rn(t.y, __fmul_rn(nw, __fmul_rn(x.y, n)));
+    t.z = __fsub_rn(t.z, __fmul_rn(nw, __fmul_rn(x.z, n)));
+    t.w = __fsub_rn(t.w, __fmul_rn(nw, __fmul_rn(x.w, n)));
+}
+
+#ifndef DCRF_TUNE_REF_MINB
+#define DCRF_TUNE_REF_MINB 6
+#endif
+template <int G, int DA, int DB>
+__global__ void __launch_bounds__(kThreads, G ? DCRF_TUNE_REF_MINB : 1) slice_softmax_ref_kernel(
+    const SliceArgs a, const float4 *__restrict__ unary4, float4 *__restrict__ Q4, unsigned Ntot, int L, int g_rt) {
+    const RowMap<G> rm(g_rt);
+    const unsigned g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
+    const unsigned p = act ? (unsigned)p64 : 0u;
+    const SliceTerm &t0 = a.term[0];
+    const SliceTerm &t1 = a.term[1];
+    const int gb = (int)(threadIdx.x & 31) - (int)c;
+    float4 x0, x1;
+    if (G >= 3) {
+        x0 = slice_ref_row_coop<DA, (G >= 3 ? G : 3)>(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, c, gb);
+        x1 = slice_ref_row_coop<DB, (G >= 3 ? G : 3)>(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, c, gb);
+    } else {
+        x0 = slice_ref_row_rt(t0.ent, reinterpret_cast<const float4 *>(t0.val), p, DA, g, c);
+        x1 = slice_ref_row_rt(t1.ent, reinterpret_cast<const float4 *>(t1.val), p, DB, g, c);
+    }
+    const float4 u = __ldg(unary4 + (p * g + c));
+    const float n0 = t0.norm ? __ldg(t0.norm + p) : 1.0f;  // x * 1.0f is exact
+    const float n1 = t1.norm ? __ldg(t1.norm + p) : 1.0f;
+    float4 t = make_float4(-u.x, -u.y, -u.z, -u.w);
+    sub_potts(t, x0, n0, t0.potts_w);
+    sub_potts(t, x1, n1, t1.potts_w);
+    const ExpfRef ex;
+    const float4 q = softmax_ref_row<G>(t, L, (int)c, (int)g, gb, ex);
+    if (act) Q4[p * g + c] = q;
+}
+
+// any other combination of Potts terms (0..4 terms, any dimensions; n_terms = 0 is startInference)
+template <int G>
+__global__ void __launch_bounds__(kThreads) slice_softmax_ref_generic_kernel(
+    const SliceArgs a, const float4 *__restrict__ unary4, float4 *__restrict__ Q4, unsigned Ntot, int L, int g_rt) {
+    const RowMap<G> rm(g_rt);
+    const unsigned g = rm.g, c = rm.col();
+    const int64_t p64 = rm.row();
+    const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
+    const unsigned p = act ? (unsigned)p64 : 0u;
+    const int gb = (int)(threadIdx.x & 31) - (int)c;
+    const float4 u = __ldg(unary4 + (p * g + c));
+    float4 t = make_float4(-u.x, -u.y, -u.z, -u.w);
+    for (int k = 0; k < a.n_terms; k++) {
+        const SliceTerm &tm = a.term[k];
+        const float4 x = slice_ref_row_rt(tm.ent, reinterpret_cast<const float4 *>(tm.val), p, tm.d, g, c);
+        const float n = tm.norm ? __ldg(tm.norm + p) : 1.0f;
+        sub_potts(t, x, n, tm.potts_w);
+    }
+    const ExpfRef ex;
+    const float4 q = softmax_ref_row<G>(t, L, (int)c, (int)g, gb, ex);
+    if (act) Q4[p * g + c] = q;
 }
 
 // slice of one lattice without any epilogue (norm construction, test hook)
@@ -1213,25 +1347,44 @@ void launch_splat(const Lattice &lat, const float *Q, const float *norm_pre, flo
 }
 
 void launch_find_long_rows(Lattice &lat, cudaStream_t s) {
-    lat.long_rows.alloc((size_t)(lat.E / kSplatLongRow + 1), s);
+    if (lat.long_row_cap <= 0) lat.long_row_cap = kSplatLongRow;
+    lat.long_rows.alloc((size_t)(lat.E / lat.long_row_cap + 1), s);
     lat.n_long.alloc(1, s);
     DCRF_CUDA(cudaMemsetAsync(lat.n_long.p, 0, sizeof(int), s));
     if (lat.M == 0) return;
     find_long_rows_kernel<<<ceil_div(lat.M, kThreads), kThreads, 0, s>>>(lat.csr_start.p, lat.M, lat.long_rows.p,
-                                                                      lat.n_long.p);
+                                                                      lat.n_long.p, lat.long_row_cap);
     DCRF_LAUNCHED();
 }
 
 void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *norm_post, cudaStream_t s) {
     if (lat.E == 0) return;
+    lat.csr_ent4.release();
     lat.ent.alloc(lat.E, s);
     lat.csr_ent.alloc(lat.E, s);
     lat.row_counter.alloc(1, s);
+    lat.long_row_cap = kSplatLongRow;
     launch_find_long_rows(lat, s);
     pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
         lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, norm_post, lat.d + 1, lat.ent.p,
         lat.csr_ent.p, lat.E);
     DCRF_LAUNCHED();
+    lat.table_mode = kTablesFma;
+}
+
+void launch_pack_ref_tables(Lattice &lat, const float *norm_pre, int long_row_cap, cudaStream_t s) {
+    if (lat.E == 0) return;
+    lat.csr_ent.release();
+    lat.ent.alloc(lat.E, s);
+    lat.csr_ent4.alloc(lat.E, s);
+    lat.row_counter.alloc(1, s);
+    lat.long_row_cap = long_row_cap > 0 ? long_row_cap : kSplatLongRow;
+    launch_find_long_rows(lat, s);
+    const float alpha = 1.0f / (1.0f + powf(2.0f, (float)-lat.d));
+    pack_ref_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
+        lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, alpha, lat.ent.p, lat.csr_ent4.p, lat.E);
+    DCRF_LAUNCHED();
+    lat.table_mode = kTablesRef;
 }
 
 template <typename K>
@@ -1241,27 +1394,34 @@ static int resident_blocks_per_sm(K kernel) {
     return n > 0 ? n : 1;
 }
 
-void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
-    if (lat.M == 0) return;
+// REF = false: FMA tables (csr_ent); REF = true: reference-association tables (csr_ent4)
+template <bool REF>
+static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
+    typedef typename CsrEnt<REF>::type Ent;
     const int g = Lp / 4;
+    const Ent *ents;
+    if (REF) ents = reinterpret_cast<const Ent *>(lat.csr_ent4.p);
+    else ents = reinterpret_cast<const Ent *>(lat.csr_ent.p);
+    const int cap = lat.long_row_cap;
     DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, sizeof(int), s));
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     // entries per trip: long rows (Gaussian lattice, ~23 entries) amortise the loop overhead over 8
     // entries, short skewed rows (bilateral lattice, median 6) waste fewer predicated slots with 4
     const bool long_rows = lat.E >= 16 * lat.M;
+    const float4 *q4 = reinterpret_cast<const float4 *>(Q);
+    float4 *v4 = reinterpret_cast<float4 *>(val);
     // 4 <= G <= 8 (13..32 labels): cooperative entry loads, G entries per trip (bilateral splat of the
     // VOC batch: 417 us against 463 us for splat_fast_kernel<6, 4>, Gaussian 206 against 218 <6, 8>)
     if (g >= 4 && g <= 8) {
-        const float4 *q4 = reinterpret_cast<const float4 *>(Q);
-        float4 *v4 = reinterpret_cast<float4 *>(val);
 #define DCRF_COOP_LAUNCH(GG, MINB)                                                                          \
     case GG: {                                                                                              \
-        static const int per_sm = resident_blocks_per_sm(splat_coop_kernel<GG, 1, MINB>);                   \
+        constexpr int MB = (REF && kSplatRefMinBlocks) ? kSplatRefMinBlocks : MINB;                         \
+        static const int per_sm = resident_blocks_per_sm(splat_coop_kernel<GG, 1, MB, REF>);                \
         const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);   \
-        splat_coop_kernel<GG, 1, MINB><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_ent.p, q4, v4,     \
-                                                               (int)lat.M, lat.row_counter.p);             \
-        splat_long_tail_kernel<GG><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(               \
-            lat.csr_start.p, lat.csr_ent.p, q4, v4, lat.long_rows.p, lat.n_long.p, g);                     \
+        splat_coop_kernel<GG, 1, MB, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4,           \
+                                                                  (int)lat.M, lat.row_counter.p, cap);     \
+        splat_long_tail_kernel<GG, REF><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(          \
+            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap);                         \
     } break;
         switch (g) {
             DCRF_COOP_LAUNCH(4, 5)
@@ -1278,27 +1438,29 @@ void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, c
     DCRF_DISPATCH_G(g, {
         // persistent grid of exactly one resident wave; rows are claimed dynamically
         if (long_rows) {
-            static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, 8>);
+            static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, 8, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
-            splat_fast_kernel<G, 8><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_ent.p,
-                                                           reinterpret_cast<const float4 *>(Q),
-                                                           reinterpret_cast<float4 *>(val), (int)lat.M, g,
-                                                           lat.row_counter.p);
+            splat_fast_kernel<G, 8, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4, (int)lat.M, g,
+                                                                lat.row_counter.p, cap);
         } else {
-            static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, kSplatBatch>);
+            static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, kSplatBatch, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
-            splat_fast_kernel<G, kSplatBatch><<<nb, kThreads, 0, s>>>(lat.csr_start.p, lat.csr_ent.p,
-                                                                     reinterpret_cast<const float4 *>(Q),
-                                                                     reinterpret_cast<float4 *>(val), (int)lat.M,
-                                                                     g, lat.row_counter.p);
+            splat_fast_kernel<G, kSplatBatch, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4,
+                                                                          (int)lat.M, g, lat.row_counter.p, cap);
         }
         // tail of very long rows (no-op grid when the lattice has none; the count lives on the device)
-        splat_long_tail_kernel<G><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(
-            lat.csr_start.p, lat.csr_ent.p, reinterpret_cast<const float4 *>(Q), reinterpret_cast<float4 *>(val),
-            lat.long_rows.p, lat.n_long.p, g);
+        splat_long_tail_kernel<G, REF><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(
+            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap);
     });
     DCRF_LAUNCHED();
     g_launches.fetch_add(1);
+}
+
+void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
+    if (lat.M == 0) return;
+    DCRF_REQUIRE(lat.table_mode != kTablesNone, DCRF_ESTATE, "packed lattice tables are missing");
+    if (lat.table_mode == kTablesRef) launch_splat_packed<true>(lat, Q, val, Lp, s);
+    else launch_splat_packed<false>(lat, Q, val, Lp, s);
 }
 
 void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int Lp, bool seq,
@@ -1322,32 +1484,30 @@ void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int6
     const int nb = ceil_div(Ntot, rows_per_block(g));
     ProfScope prof(DCRF_K_SLICE, a.n_terms, s);
     const bool fast25 = a.n_terms == 2 && a.term[0].d == 2 && a.term[1].d == 5 && !a.seq;
-    const bool potts2 = fast25 && a.term[0].compat_kind == DCRF_COMPAT_POTTS &&
-                        a.term[1].compat_kind == DCRF_COMPAT_POTTS && a.term[0].ent && a.term[1].ent;
-    if (a.fast && a.n_terms == 0 && !a.seq && Ntot * g < ((int64_t)1 << 31)) {
-        DCRF_DISPATCH_G(g, {
-            softmax_unary_fast_kernel<G><<<nb, kThreads, 0, s>>>(reinterpret_cast<const float4 *>(unary),
-                                                               reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
-        });
-        DCRF_LAUNCHED();
-        return;
-    }
-    if (a.fast && potts2 && Ntot * g < ((int64_t)1 << 31)) {
-        DCRF_DISPATCH_G(g, {
-            slice_softmax_fast_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(
-                a, reinterpret_cast<const float4 *>(unary), reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
-        });
-        DCRF_LAUNCHED();
-        return;
-    }
-    bool all_potts = a.n_terms >= 1 && !a.seq;
+    bool all_potts = !a.seq;
     for (int k = 0; k < a.n_terms; k++)
         all_potts = all_potts && a.term[k].compat_kind == DCRF_COMPAT_POTTS && a.term[k].ent != nullptr;
-    if (a.fast && all_potts && Ntot * g < ((int64_t)1 << 31)) {
-        DCRF_DISPATCH_G(g, {
-            slice_softmax_fast_generic_kernel<G><<<nb, kThreads, 0, s>>>(
-                a, reinterpret_cast<const float4 *>(unary), reinterpret_cast<float4 *>(Q), (unsigned)Ntot, L, g);
-        });
+    // the packed-table kernels index rows with 32 bits: largest row index * g must stay below 2^32
+    const bool idx32 = a.max_rows * (int64_t)g < ((int64_t)1 << 32) && Ntot * (int64_t)g < ((int64_t)1 << 31);
+    const float4 *u4 = reinterpret_cast<const float4 *>(unary);
+    float4 *q4 = reinterpret_cast<float4 *>(Q);
+    if (a.fast == kSliceRef && all_potts && idx32) {
+        if (fast25) {
+            DCRF_DISPATCH_G(g, { slice_softmax_ref_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(a, u4, q4, (unsigned)Ntot, L, g); });
+        } else {
+            DCRF_DISPATCH_G(g, { slice_softmax_ref_generic_kernel<G><<<nb, kThreads, 0, s>>>(a, u4, q4, (unsigned)Ntot, L, g); });
+        }
+        DCRF_LAUNCHED();
+        return;
+    }
+    if (a.fast == kSliceFma && all_potts && idx32) {
+        if (a.n_terms == 0) {
+            DCRF_DISPATCH_G(g, { softmax_unary_fast_kernel<G><<<nb, kThreads, 0, s>>>(u4, q4, (unsigned)Ntot, L, g); });
+        } else if (fast25) {
+            DCRF_DISPATCH_G(g, { slice_softmax_fast_kernel<G, 2, 5><<<nb, kThreads, 0, s>>>(a, u4, q4, (unsigned)Ntot, L, g); });
+        } else {
+            DCRF_DISPATCH_G(g, { slice_softmax_fast_generic_kernel<G><<<nb, kThreads, 0, s>>>(a, u4, q4, (unsigned)Ntot, L, g); });
+        }
         DCRF_LAUNCHED();
         return;
     }
@@ -1484,6 +1644,20 @@ void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, f
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s) {
     if (Ntot == 0) return;
     argmax_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(pm, labels, Ntot, L, Lp);
+    DCRF_LAUNCHED();
+}
+
+// test hook: y[i] = ExpfRef(x[i]) (warp-collective, so whole warps run and only the store is guarded)
+__global__ void __launch_bounds__(kThreads) expf_ref_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                            int64_t n) {
+    const ExpfRef ex;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const float r = ex(i < n ? x[i] : 0.f);
+    if (i < n) y[i] = r;
+}
+void launch_expf_ref(const float *x, float *y, int64_t n, cudaStream_t s) {
+    if (n == 0) return;
+    expf_ref_kernel<<<ceil_div(n, kThreads), kThreads, 0, s>>>(x, y, n);
     DCRF_LAUNCHED();
 }
 

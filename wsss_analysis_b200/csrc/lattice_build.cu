@@ -536,6 +536,16 @@ __global__ void __launch_bounds__(kThreads) rep_i2_kernel(const int2 *__restrict
     if (shift_y && v.y >= 0) v.y = (int32_t)(v.y + (int64_t)blockIdx.y * shift_y);
     out[(int64_t)blockIdx.y * n + i] = v;
 }
+// packed reference entries (pixel, w, norm, -): pixel shifted, payload copied
+__global__ void __launch_bounds__(kThreads) rep_i4x_kernel(const int4 *__restrict__ in, int4 *__restrict__ out,
+                                                           int64_t n, int64_t shift_x) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    int4 v = in[i];
+    v.x = (int32_t)(v.x + (int64_t)blockIdx.y * shift_x);
+    out[(int64_t)blockIdx.y * n + i] = v;
+}
+__global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
 __global__ void __launch_bounds__(kThreads) rep_f32_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                            int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -579,7 +589,8 @@ void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, 
     out.csr_pix.alloc(out.E, s);
     out.csr_w.alloc(out.E, s);
     out.ent.alloc(out.E, s);
-    out.csr_ent.alloc(out.E, s);
+    out.table_mode = one.table_mode;
+    out.long_row_cap = one.long_row_cap;
     auto grid = [&](int64_t n) { return dim3(ceil_div(n, kThreads), B); };
     rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.offset.p, out.offset.p, E, M);
     DCRF_LAUNCHED();
@@ -593,16 +604,21 @@ void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, 
     // csr_start has M+1 entries per image; entry M of image b coincides with entry 0 of image b+1
     rep_i32_kernel<<<grid(M), kThreads, 0, s>>>(one.csr_start.p, out.csr_start.p, M, E);
     DCRF_LAUNCHED();
-    const int32_t total = (int32_t)out.E;
-    DCRF_CUDA(cudaMemcpyAsync(out.csr_start.p + out.M, &total, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    DCRF_CUDA(cudaStreamSynchronize(s));  // `total` is a stack variable
+    set_i32_kernel<<<1, 1, 0, s>>>(out.csr_start.p + out.M, (int32_t)out.E);
+    DCRF_LAUNCHED();
     rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_pix.p, out.csr_pix.p, E, n_img);
     DCRF_LAUNCHED();
     rep_f32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_w.p, out.csr_w.p, E);
     DCRF_LAUNCHED();
     rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.ent.p, out.ent.p, E, M, 0);
     DCRF_LAUNCHED();
-    rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, E, n_img, 0);
+    if (one.table_mode == kTablesRef) {
+        out.csr_ent4.alloc(out.E, s);
+        rep_i4x_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent4.p, out.csr_ent4.p, E, n_img);
+    } else {
+        out.csr_ent.alloc(out.E, s);
+        rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, E, n_img, 0);
+    }
     DCRF_LAUNCHED();
     if (one.row_counter.p) out.row_counter.alloc(1, s);
     launch_find_long_rows(out, s);
