@@ -94,19 +94,25 @@ int dcrf_create_batch(int n_images, const int *w, const int *h, int n_labels, in
 void dcrf_destroy(dcrf_t *h);
 
 /* Options.  DCRF_OPT_EXACT_ARITHMETIC selects the float arithmetic of the per-iteration kernels:
- *   DCRF_ARITH_REFERENCE (1, default): the association of the sequential CPU evaluation [EXT],
- *     operation for operation -- separately rounded multiply / add in splat and slice, normalisation
- *     applied as its own rounded product, expf as the host libm (glibc) evaluates it, softmax sum in
- *     label order, IEEE division.  Marginals are bit-identical to such an evaluation, with one
- *     exception: splat rows with more than 256 entries (flat image regions) are summed as 256
- *     sequential terms + a fixed tree over the tail.
+ *   DCRF_ARITH_FMA (0): fused multiply-add, normalisation folded into the packed entry weights, one
+ *     reciprocal per softmax, CUDA expf.  Differs from a sequential CPU evaluation [EXT] by float
+ *     rounding only (<= 1e-5 on Q for well-conditioned models).
+ *   DCRF_ARITH_REFERENCE (1): the association of the sequential CPU evaluation, operation for
+ *     operation -- separately rounded multiply / add in splat and slice, normalisation applied as its
+ *     own rounded product, expf as the host libm (glibc) evaluates it, softmax sum in label order,
+ *     IEEE division.  Marginals are bit-identical to such an evaluation, with one exception: splat
+ *     rows with more than 256 entries (flat image regions) are summed as 256 sequential terms + a
+ *     fixed tree over the tail.  About 20 % slower per iteration than DCRF_ARITH_FMA.
  *   DCRF_ARITH_STRICT (2): as 1 without that exception (a lattice vertex shared by thousands of
  *     pixels is then summed by one lane group: slow on flat images).
- *   DCRF_ARITH_FMA (0): fused multiply-add, normalisation folded into the packed entry weights, one
- *     reciprocal per softmax, CUDA expf.  Differs from the others by float rounding only.
- * All modes are run-to-run deterministic.  The environment variable DCRF_ARITHMETIC = fma | reference
- * | strict overrides the default of handles created afterwards. */
-enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2 };
+ *   DCRF_ARITH_AUTO (3, default): DCRF_ARITH_REFERENCE for models with a narrow appearance kernel
+ *     (any bilateral colour bandwidth below 8, e.g. the IRN label CRF with srgb = 5 or SEC's ADP-func
+ *     setting with srgb = 4: there the mean-field update is expansive at bistable pixels and
+ *     rounding differences grow from iteration to iteration), DCRF_ARITH_FMA otherwise.
+ * All modes are run-to-run deterministic.  The environment variable DCRF_ARITHMETIC = auto | fma |
+ * reference | strict sets the default of handles created afterwards.  dcrf_get_arithmetic returns
+ * the mode the handle resolved to (0, 1 or 2). */
+enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2, DCRF_ARITH_AUTO = 3 };
 /* DCRF_OPT_ASYNC_HOST = 1: calls that read or write caller HOST buffers only enqueue their copies on
  * the handle's stream and return; the caller keeps the buffers alive and untouched until
  * dcrf_synchronize().  Lets one host thread keep two handles (two streams) in flight so that the
@@ -116,6 +122,7 @@ enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2 };
  * builds enqueued next overlap the upload; the handle's stream waits for it before the unary is read. */
 enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2 };
 int dcrf_set_option(dcrf_t *h, int option, int value);
+int dcrf_get_arithmetic(dcrf_t *h, int *mode_out);
 /* block the calling thread until everything enqueued on the handle's stream has finished */
 int dcrf_synchronize(dcrf_t *h);
 
@@ -131,7 +138,8 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device);
  *    has_clip = 1, clip = 1e-5 are the defaults the reference uses.
  *  - from a feature map: SEC/DSRG `crf_inference(..., use_log=True)` ([EXT] lib/crf.py; call sites
  *    03a_sec-dsrg/SEC.py:275, model.py:689): feat = concatenated (H_b, W_b, L) float32 blocks,
- *    U = -log softmax_L(feat) (use_log) or -log(feat).
+ *    U = -log softmax_L(feat).  use_log must be non-zero: the wrapper's other branch is exercised by
+ *    no call site and its source is not in the reference tree, so it is not guessed (DCRF_EINVAL).
  *  - from hard labels: `unary_from_labels(labels, L, gt_prob, zero_unsure)` [EXT] as used by
  *    crf_inference_label (03b_irn/step/cam_to_ir_label.py:35).  labels: concatenated int32. */
 int dcrf_set_unary_from_probs(dcrf_t *h, const void *probs, int is_f64, double scale, double clip,
@@ -165,6 +173,10 @@ int dcrf_inference(dcrf_t *h, int n_iter, float *Q_out, int on_device);
  * replaces `np.argmax(np.array(Q).reshape(L,H,W), axis=0)` (03c_hsn/utilities.py:443-444,
  * [EXT] crf_inference_label used by 03b_irn/step/cam_to_ir_label.py:35).  labels: sum(N_b) int32. */
 int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device);
+/* the same with uint8 labels (n_labels <= 256): what a label consumer downloads -- 1 byte per pixel
+ * over PCIe instead of 4 * n_labels bytes of marginals (dcrf_process, crf_inference_label, the
+ * evaluation loops of 03a_sec-dsrg/model.py:699 and 03b_irn/step/eval_sem_seg.py only keep argmax) */
+int dcrf_map_u8(dcrf_t *h, int n_iter, uint8_t *labels_out, int on_device);
 
 /* The two halves of dcrf_inference / dcrf_map, for callers that overlap the download of one batch
  * with the iterations of the next (wsss_analysis_b200/pipeline.py): dcrf_run = startInference +
@@ -172,6 +184,7 @@ int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device);
  * running Q (or its argmax). */
 int dcrf_run(dcrf_t *h, int n_iter);
 int dcrf_get_labels(dcrf_t *h, int32_t *labels_out, int on_device);
+int dcrf_get_labels_u8(dcrf_t *h, uint8_t *labels_out, int on_device);
 
 /* [EXT] startInference / stepInference / klDivergence.  The running Q lives inside the handle. */
 int dcrf_start_inference(dcrf_t *h);

@@ -1,7 +1,8 @@
-"""GPU: the default ("reference") arithmetic of the iteration kernels is bit-identical to the CPU
-oracle -- same float association in splat / blur / slice, libm-identical expf, softmax sum in label
-order, IEEE division -- so the marginals agree bit for bit, whatever the conditioning of the
-mean-field map.  PARITY UNPINNED: the oracle is this repo's restatement of pydensecrf."""
+"""GPU: the "reference" arithmetic of the iteration kernels is bit-identical to the CPU oracle --
+same float association in splat / blur / slice, libm-identical expf, softmax sum in label order,
+IEEE division -- so the marginals agree bit for bit, whatever the conditioning of the mean-field
+map.  The default ("auto") selects it for models with a narrow appearance kernel and the faster FMA
+kernels otherwise (include/dcrf_b200.h, DCRF_OPT_EXACT_ARITHMETIC).  PARITY UNPINNED: the oracle is this repo's restatement of pydensecrf."""
 import numpy as np
 import pytest
 
@@ -84,9 +85,11 @@ def test_deepglobe_612_irn_bit_identical_where_fma_drifts():
     L = 6
     img = S.natural_image(H, W, 4)
     U = S.random_unary(L, W * H, 4)
-    o, (g, gf) = _models(W, H, L, 3, 3, 50, 5, 10, img, U, modes=("reference", "fma"))
+    o, (g, gf, ga) = _models(W, H, L, 3, 3, 50, 5, 10, img, U, modes=("reference", "fma", "auto"))
     Qo, Qg, Qf = o.inference(10), g.inference(10), gf.inference(10)
     assert np.array_equal(_bits(Qo), _bits(Qg))
+    # the default policy picks the reference arithmetic for this narrow appearance kernel (srgb = 5)
+    assert ga.arithmetic() == "reference" and np.array_equal(_bits(ga.inference(10)), _bits(Qo))
     dmax = np.abs(Qo - Qf).max(0)
     assert (dmax <= 1e-4).mean() >= 0.9999 and dmax.max() <= 1e-3
     assert (Qo.argmax(0) == Qf.argmax(0)).mean() >= 0.999
@@ -104,11 +107,16 @@ def test_voc_batch_of_32_one_step_vs_oracle():
     W, H, L, B = 500, 375, 21, 32
     imgs = [S.natural_image(H, W, 100 + b) for b in range(B)]
     Us = [S.random_unary(L, W * H, 100 + b) for b in range(B)]
-    d = G.DenseCRFBatch([(W, H)] * B, L)
-    d.setUnaryEnergy(Us)
-    d.addPairwiseGaussian(sxy=3, compat=3)
-    d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=imgs, compat=10)
-    Qg = d.inference(10)
+    Q = {}
+    for mode in ("auto", "strict"):
+        d = G.DenseCRFBatch([(W, H)] * B, L)
+        d.set_arithmetic(mode)
+        d.setUnaryEnergy(Us)
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=imgs, compat=10)
+        Q[mode] = d.inference(10)
+        assert d.arithmetic() == ("fma" if mode == "auto" else "strict")   # what bench.py's headline runs
+        d.close()
 
     def cpu(b):
         o = O.DenseCRF2D(W, H, L)
@@ -120,7 +128,9 @@ def test_voc_batch_of_32_one_step_vs_oracle():
     with ThreadPoolExecutor(max_workers=16) as ex:
         Qo = list(ex.map(cpu, range(B)))
     for b in range(B):
-        assert np.array_equal(_bits(Qo[b]), _bits(Qg[b])), (b, float(np.abs(Qo[b] - Qg[b]).max()))
+        assert np.array_equal(_bits(Qo[b]), _bits(Q["strict"][b])), (b, float(np.abs(Qo[b] - Q["strict"][b]).max()))
+        assert np.abs(Qo[b] - Q["auto"][b]).max() <= 1e-4
+        assert (Qo[b].argmax(0) == Q["auto"][b].argmax(0)).mean() >= 0.999
 
 
 def test_adp_1088_morph_29_labels_vs_oracle():
@@ -132,13 +142,15 @@ def test_adp_1088_morph_29_labels_vs_oracle():
     L = 29
     img = S.histo_image(H, W, 2, n_blobs=25)
     U = S.random_unary(L, W * H, 2)
-    o, (g,) = _models(W, H, L, 1, 20, 10, 40, 50, img, U)
+    o, (g, ga) = _models(W, H, L, 1, 20, 10, 40, 50, img, U, modes=("reference", "auto"))
     for k in range(2):
         eo, eg = o.lattice(k), g.lattice_export(k)
         assert eo.M == eg["M"] and np.array_equal(eo.offsets, eg["offsets"])
         assert np.array_equal(eo.neighbours, eg["neighbours"]) and np.array_equal(eo.keys, eg["keys"])
-    Qo, Qg = o.inference(5), g.inference(5)
+    Qo, Qg, Qa = o.inference(5), g.inference(5), ga.inference(5)
     assert np.abs(Qo - Qg).max() <= 1e-4 and (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999
+    assert ga.arithmetic() == "fma"
+    assert np.abs(Qo - Qa).max() <= 1e-4 and (Qo.argmax(0) == Qa.argmax(0)).mean() >= 0.999
     # histology backgrounds are near-flat: rows longer than 256 entries exist, whose tails the default
     # mode sums by a tree; everything else is bit-identical
     assert (_bits(Qo) == _bits(Qg)).mean() >= 0.99
@@ -152,16 +164,18 @@ def test_deepglobe_2448_vs_oracle():
     L = 6
     img = S.natural_image(H, W, 3)
     U = S.random_unary(L, W * H, 3)
-    o, (g,) = _models(W, H, L, 3, 3, 80, 13, 10, img, U)
+    o, (g, ga) = _models(W, H, L, 3, 3, 80, 13, 10, img, U, modes=("reference", "auto"))
     assert o.lattice(1).M == g.lattice_export(1, with_norm=False)["M"]
-    Qo, Qg = o.inference(10), g.inference(10)
+    Qo, Qg, Qa = o.inference(10), g.inference(10), ga.inference(10)
     assert np.abs(Qo - Qg).max() <= 1e-4 and (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999
     assert (_bits(Qo) == _bits(Qg)).mean() >= 0.99
+    assert ga.arithmetic() == "fma"
+    assert np.abs(Qo - Qa).max() <= 1e-4 and (Qo.argmax(0) == Qa.argmax(0)).mean() >= 0.999
 
 
 def test_strict_mode_is_bit_identical_on_flat_images():
     """A flat image collapses the bilateral lattice to a few vertices with thousands of entries each;
-    "strict" sums every row sequentially like the CPU, the default cuts rows at 256 entries."""
+    "strict" sums every row sequentially like the CPU, "reference" cuts rows at 256 entries."""
     from wsss_analysis_b200 import synthetic as S
 
     W, H, L = 160, 120, 21

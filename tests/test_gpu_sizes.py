@@ -123,8 +123,10 @@ def test_deepglobe_612_vs_oracle():
     assert o.lattice(1).M == g.lattice_export(1)["M"]
     # Pure-noise unaries + srgb = 5 + 10 iterations make the mean-field map expansive at a handful
     # of bistable pixels (rounding differences grow ~2.5x per iteration).  The
-    # default arithmetic follows the oracle operation for operation, so BASELINE's 1e-4 holds with
-    # room to spare (tests/test_gpu_reference_arith.py asserts bit identity and covers the FMA mode).
+    # default policy runs such narrow-appearance-kernel models (srgb = 5) with the reference
+    # arithmetic, which follows the oracle operation for operation, so BASELINE's 1e-4 holds with room
+    # to spare (tests/test_gpu_reference_arith.py asserts bit identity and covers the FMA mode).
+    assert g.arithmetic() == "reference"
     assert np.abs(Qo - Qx).max() <= 1e-4
     assert np.abs(Qo - Qg).max() <= 1e-4
     assert (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999

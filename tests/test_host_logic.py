@@ -133,6 +133,31 @@ def test_bench_algorithmic_bytes_formula():
     survey = 12 * L * N + sum(16 * (d + 1) * N + 8 * L * M + (d + 1) * (8 * L * M + 8 * M) for d, M in ((2, Mg), (5, Mb)))
     extra = 4 * L * N + 4 * (Mg + Mb)
     assert per_iter == survey + extra
+    assert bench.iteration_bytes(N, L, [(2, Mg), (5, Mb)]) == survey
+
+
+def test_bench_configs_cover_baseline_and_both_arms_share_the_config():
+    """Every BASELINE.json configuration has a bench entry with the reference's CRF parameters
+    (SURVEY.md Appendix B), and the CPU reference arm describes its workload with the same `config`
+    object as the CUDA arm (the driver compares them)."""
+    import bench
+
+    C = bench.CONFIGS
+    assert list(C)[0] == bench.HEADLINE == "voc32"
+    assert {"voc32", "voc1", "sec41x32", "hsn321x16", "adp1088_morph", "adp1088_func", "dg612x8", "dg2448"} <= set(C)
+    v = C["voc32"]
+    assert (v["sizes"][0], v["L"], v["iters"], v["g_sxy"], v["g_compat"], v["b_sxy"], v["b_srgb"], v["b_compat"]) == \
+        ((500, 375), 21, 10, 3.0, 3.0, 80.0, 13.0, 10.0)                      # 03a_sec-dsrg/SEC.py:20
+    s_ = C["sec41x32"]
+    assert (s_["sizes"][0], s_["iters"], s_["g_sxy"], s_["b_sxy"]) == ((41, 41), 5, 3.0 / 12, 80.0 / 12)   # SEC.py:19
+    assert (C["adp1088_morph"]["L"], C["adp1088_func"]["L"], C["dg2448"]["L"]) == (29, 5, 6)
+    assert (C["dg612x8"]["b_sxy"], C["dg612x8"]["b_srgb"]) == (50.0, 5.0)    # IRN crf_inference_label defaults
+    assert C["dg2448"]["sizes"] == [(2448, 2448)]
+    assert bench.SWEEP_IMAGES == 1449
+    for name, cfg in C.items():
+        d = bench.config_dict(name, cfg)
+        assert d["name"] == name and d["images_per_gpu_per_step"] == len(cfg["sizes"]) and "impl" not in d
+        assert bench.npix(cfg) * 6 < 2 ** 31                                 # one handle per step
 
 
 def test_wrapper_batches_are_chunked_below_the_int32_entry_limit(monkeypatch):

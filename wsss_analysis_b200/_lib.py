@@ -26,6 +26,7 @@ SIGNATURES = {
     "dcrf_create_batch": (_i, [_i, _vp, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "dcrf_destroy": (None, [_vp]),
     "dcrf_set_option": (_i, [_vp, _i, _i]),
+    "dcrf_get_arithmetic": (_i, [_vp, C.POINTER(_i)]),
     "dcrf_synchronize": (_i, [_vp]),
     "dcrf_set_unary": (_i, [_vp, _vp, _i]),
     "dcrf_set_unary_from_probs": (_i, [_vp, _vp, _i, C.c_double, C.c_double, _i, _i]),
@@ -36,8 +37,10 @@ SIGNATURES = {
     "dcrf_add_pairwise_energy": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i]),
     "dcrf_inference": (_i, [_vp, _i, _vp, _i]),
     "dcrf_map": (_i, [_vp, _i, _vp, _i]),
+    "dcrf_map_u8": (_i, [_vp, _i, _vp, _i]),
     "dcrf_run": (_i, [_vp, _i]),
     "dcrf_get_labels": (_i, [_vp, _vp, _i]),
+    "dcrf_get_labels_u8": (_i, [_vp, _vp, _i]),
     "dcrf_start_inference": (_i, [_vp]),
     "dcrf_step_inference": (_i, [_vp]),
     "dcrf_get_q": (_i, [_vp, _vp, _i]),

@@ -113,6 +113,7 @@ struct Pairwise {
     int ntype = DCRF_NORMALIZE_SYMMETRIC, ktype = DCRF_DIAG_KERNEL;
     int compat_kind = DCRF_COMPAT_POTTS;
     float potts_w = 0.f;
+    bool stiff = false;  // narrow appearance kernel (see auto_arith)
 };
 
 }  // namespace dcrf
@@ -129,7 +130,8 @@ struct dcrf_handle {
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
     bool unary_set = false, q_valid = false;
-    int arith = kArithFma;    // DCRF_OPT_EXACT_ARITHMETIC: kArithFma / kArithRef / kArithStrict
+    int arith = kArithFma;    // resolved arithmetic: kArithFma / kArithRef / kArithStrict
+    bool arith_auto = true;   // DCRF_ARITH_AUTO: `arith` follows the conditioning of the pairwise terms
     bool async_host = false;  // DCRF_OPT_ASYNC_HOST
     std::vector<std::unique_ptr<Pairwise>> pw;
     Profiler prof;
@@ -193,15 +195,29 @@ void join_upload(dcrf_handle *h) {
 
 int64_t total_ln(const dcrf_handle *h) { return h->geom.Ntot * (int64_t)h->L; }
 
-// default arithmetic of new handles: reference association unless DCRF_ARITHMETIC says otherwise
+// default arithmetic of new handles: DCRF_ARITH_AUTO unless DCRF_ARITHMETIC says otherwise
 int default_arith() {
     const char *e = getenv("DCRF_ARITHMETIC");
-    if (!e || !*e) return kArithRef;
+    if (!e || !*e || !strcmp(e, "auto") || !strcmp(e, "3")) return DCRF_ARITH_AUTO;
     if (!strcmp(e, "fma") || !strcmp(e, "0")) return kArithFma;
     if (!strcmp(e, "strict") || !strcmp(e, "2")) return kArithStrict;
     DCRF_REQUIRE(!strcmp(e, "reference") || !strcmp(e, "1"), DCRF_EINVAL,
-                 "DCRF_ARITHMETIC must be fma, reference or strict");
+                 "DCRF_ARITHMETIC must be auto, fma, reference or strict");
     return kArithRef;
+}
+void set_arith(dcrf_handle *h, int mode) {
+    h->arith_auto = mode == DCRF_ARITH_AUTO;
+    if (!h->arith_auto) h->arith = mode;
+}
+// DCRF_ARITH_AUTO: a narrow appearance kernel (colour bandwidth below 8 grey levels: the IRN label CRF,
+// srgb = 5, and SEC's ADP-func test setting, srgb = 4) concentrates a pixel's message on a handful of
+// neighbours; with a Potts weight of 10..25 the mean-field update is then expansive at bistable
+// pixels and float rounding differences grow ~2.5x per iteration.  Such models
+// run the reference arithmetic, whose marginals are bit-identical to the sequential evaluation; all
+// others keep the faster FMA kernels, which stay within 1e-5 of it.
+void auto_arith(dcrf_handle *h, const FeatureSpec &fs) {
+    if (!h->arith_auto || h->arith != kArithFma) return;
+    if (fs.mode == 1 && std::min(fs.s[2], std::min(fs.s[3], fs.s[4])) < 8.0f) h->arith = kArithRef;
 }
 
 void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, int device, void *stream,
@@ -231,7 +247,7 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     h->L = L;
     h->Lp = ((L + 3) / 4) * 4;
     h->has_geom = has_geom;
-    h->arith = default_arith();
+    set_arith(h.get(), default_arith());
     BatchGeom &g = h->geom;
     g.B = B;
     g.w.resize(B);
@@ -318,6 +334,8 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
     const int L = h->L, Lp = h->Lp;
     const int64_t Ntot = h->geom.Ntot;
     std::unique_ptr<Pairwise> p(new Pairwise());
+    p->stiff = fs.mode == 1 && std::min(fs.s[2], std::min(fs.s[3], fs.s[4])) < 8.0f;
+    auto_arith(h, fs);
     p->ktype = ktype;  // CONST / DIAG / FULL are all the identity feature map at default parameters
     p->ntype = ntype;
     p->compat_kind = compat_kind;
@@ -460,6 +478,25 @@ void emit_q(dcrf_handle *h, float *Q_out, int on_device) {
     }
 }
 
+// argmax of the running Q as int32 or uint8 labels, to device or host memory
+template <typename T>
+void emit_labels(dcrf_handle *h, T *labels_out, int on_device) {
+    const int64_t N = h->geom.Ntot;
+    auto launch = [&](T *dst) {
+        if (sizeof(T) == 1) launch_argmax_u8(h->Q.p, (uint8_t *)dst, N, h->L, h->Lp, h->stream);
+        else launch_argmax(h->Q.p, (int32_t *)dst, N, h->L, h->Lp, h->stream);
+    };
+    if (on_device) {
+        launch(labels_out);
+    } else {
+        DevBuf<T> stage;
+        stage.alloc(N, h->stream);
+        launch(stage.p);
+        DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(T) * N, cudaMemcpyDeviceToHost, h->stream));
+        host_sync(h);
+    }
+}
+
 void run_inference(dcrf_handle *h, int n_iter) {
     DCRF_REQUIRE(n_iter >= 0, DCRF_EINVAL, "n_iter must be >= 0");
     start_inference(h);
@@ -567,11 +604,25 @@ int dcrf_set_option(dcrf_t *h, int option, int value) {
         DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC || option == DCRF_OPT_ASYNC_HOST, DCRF_EINVAL,
                      "unknown option");
         if (option == DCRF_OPT_EXACT_ARITHMETIC) {
-            DCRF_REQUIRE(value >= 0 && value <= 2, DCRF_EINVAL, "arithmetic mode must be 0, 1 or 2");
-            h->arith = value;
+            DCRF_REQUIRE(value >= 0 && value <= 3, DCRF_EINVAL, "arithmetic mode must be 0, 1, 2 or 3");
+            if (value == DCRF_ARITH_AUTO) {  // re-derive from the terms added so far
+                h->arith_auto = true;
+                h->arith = kArithFma;
+                for (auto &p : h->pw)
+                    if (p->stiff) h->arith = kArithRef;
+            } else {
+                set_arith(h, value);
+            }
         } else {
             h->async_host = value != 0;
         }
+    });
+}
+
+int dcrf_get_arithmetic(dcrf_t *h, int *mode_out) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && mode_out, DCRF_EINVAL, "NULL argument");
+        *mode_out = h->arith;
     });
 }
 
@@ -642,6 +693,9 @@ int dcrf_set_unary_from_logits(dcrf_t *h, const float *feat, int use_log, int on
     return guarded([&] {
         DCRF_REQUIRE(h && feat, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+        // lib/crf.py is missing from the reference tree and every call site uses use_log = True
+        // (SEC.py:275, DSRG.py:328, model.py:689,693): the other branch is not guessed
+        DCRF_REQUIRE(use_log != 0, DCRF_EINVAL, "use_log = 0 is not exercised by the reference and not implemented");
         DeviceGuard guard(h->device);
         join_upload(h);
         DevBuf<float> stage;
@@ -749,17 +803,18 @@ int dcrf_map(dcrf_t *h, int n_iter, int32_t *labels_out, int on_device) {
         DeviceGuard guard(h->device);
         ProfGuard pguard(h);
         run_inference(h, n_iter);
-        const int64_t N = h->geom.Ntot;
-        if (on_device) {
-            launch_argmax(h->Q.p, labels_out, N, h->L, h->Lp, h->stream);
-        } else {
-            DevBuf<int32_t> stage;
-            stage.alloc(N, h->stream);
-            launch_argmax(h->Q.p, stage.p, N, h->L, h->Lp, h->stream);
-            DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost,
-                                      h->stream));
-            host_sync(h);
-        }
+        emit_labels(h, labels_out, on_device);
+    });
+}
+
+int dcrf_map_u8(dcrf_t *h, int n_iter, uint8_t *labels_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->L <= 256, DCRF_EINVAL, "uint8 labels need n_labels <= 256");
+        DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
+        run_inference(h, n_iter);
+        emit_labels(h, labels_out, on_device);
     });
 }
 
@@ -778,16 +833,17 @@ int dcrf_get_labels(dcrf_t *h, int32_t *labels_out, int on_device) {
         DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call dcrf_run / startInference first");
         DeviceGuard guard(h->device);
-        const int64_t N = h->geom.Ntot;
-        if (on_device) {
-            launch_argmax(h->Q.p, labels_out, N, h->L, h->Lp, h->stream);
-        } else {
-            DevBuf<int32_t> stage;
-            stage.alloc(N, h->stream);
-            launch_argmax(h->Q.p, stage.p, N, h->L, h->Lp, h->stream);
-            DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, h->stream));
-            host_sync(h);
-        }
+        emit_labels(h, labels_out, on_device);
+    });
+}
+
+int dcrf_get_labels_u8(dcrf_t *h, uint8_t *labels_out, int on_device) {
+    return guarded([&] {
+        DCRF_REQUIRE(h && labels_out, DCRF_EINVAL, "NULL argument");
+        DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call dcrf_run / startInference first");
+        DCRF_REQUIRE(h->L <= 256, DCRF_EINVAL, "uint8 labels need n_labels <= 256");
+        DeviceGuard guard(h->device);
+        emit_labels(h, labels_out, on_device);
     });
 }
 

@@ -242,6 +242,7 @@ void launch_unary_from_logits(const float *feat, float *pm, int64_t Ntot, int L,
 void launch_unary_from_labels(const int32_t *labels, float *pm, int64_t Ntot, int L, int Lp, float n_energy,
                               float p_energy, float unsure_energy, int zero_unsure, int *bad, cudaStream_t s);
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s);
+void launch_argmax_u8(const float *pm, uint8_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s);
 // out[p * L + l] = Q (pixel-major without padding, the (H, W, C) layout), optionally clamped to
 // >= min_prob and renormalised over labels in NumPy's summation order, optionally log
 void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, float min_prob, int renorm,

@@ -1250,10 +1250,10 @@ __global__ void __launch_bounds__(kThreads) unary_from_labels_kernel(const int32
     pm[i] = u;
 }
 
-// first maximum wins, like np.argmax
-__global__ void __launch_bounds__(kThreads) argmax_kernel(const float *__restrict__ pm,
-                                                          int32_t *__restrict__ labels, int64_t Ntot,
-                                                          int L, int Lp) {
+// first maximum wins, like np.argmax; T = int32_t or uint8_t (L <= 256: the form label consumers download)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) argmax_kernel(const float *__restrict__ pm, T *__restrict__ labels,
+                                                          int64_t Ntot, int L, int Lp) {
     const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (p >= Ntot) return;
     const float *row = pm + p * Lp;
@@ -1268,7 +1268,7 @@ __global__ void __launch_bounds__(kThreads) argmax_kernel(const float *__restric
             if (l < L && vv[i] > best) { best = vv[i]; bi = l; }
         }
     }
-    labels[p] = bi;
+    labels[p] = (T)bi;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1643,7 +1643,12 @@ void launch_q_to_hwc(const float *pm, float *out, int64_t Ntot, int L, int Lp, f
 
 void launch_argmax(const float *pm, int32_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s) {
     if (Ntot == 0) return;
-    argmax_kernel<<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(pm, labels, Ntot, L, Lp);
+    argmax_kernel<int32_t><<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(pm, labels, Ntot, L, Lp);
+    DCRF_LAUNCHED();
+}
+void launch_argmax_u8(const float *pm, uint8_t *labels, int64_t Ntot, int L, int Lp, cudaStream_t s) {
+    if (Ntot == 0) return;
+    argmax_kernel<uint8_t><<<ceil_div(Ntot, kThreads), kThreads, 0, s>>>(pm, labels, Ntot, L, Lp);
     DCRF_LAUNCHED();
 }
 

@@ -36,7 +36,8 @@ def _buffer(x, np_dtype, what):
     if _is_torch(x):
         import torch
 
-        want = {np.float32: torch.float32, np.uint8: torch.uint8, np.int32: torch.int32}[np_dtype]
+        want = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8,
+                np.int32: torch.int32}[np_dtype]
         if x.dtype != want:
             raise ValueError("Buffer dtype mismatch for %s: expected %s, got %s" % (what, want, x.dtype))
         if not x.is_contiguous():
@@ -125,12 +126,19 @@ class _Model(object):
             self.synchronize()
 
     def set_arithmetic(self, mode):
-        """Float arithmetic of the iteration kernels: "reference" (default: the association of the
-        sequential CPU evaluation, bit-identical marginals), "strict" (same, also for the tails of
-        splat rows longer than 256 entries) or "fma" (fused multiply-add, folded normalisation,
-        CUDA expf: rounding-level differences, a few percent faster)."""
-        code = {"fma": 0, "reference": 1, "strict": 2, 0: 0, 1: 1, 2: 2}[mode]
+        """Float arithmetic of the iteration kernels: "fma" (fused multiply-add, folded normalisation,
+        CUDA expf: rounding-level differences), "reference" (the association of the sequential CPU
+        evaluation: bit-identical marginals, ~20 % slower), "strict" (same, also for the tails of splat
+        rows longer than 256 entries) or "auto" (default: "reference" for models with a narrow
+        appearance kernel, srgb < 8, where mean field amplifies rounding differences; else "fma")."""
+        code = {"fma": 0, "reference": 1, "strict": 2, "auto": 3, 0: 0, 1: 1, 2: 2, 3: 3}[mode]
         _lib.check(self._lib.dcrf_set_option(self._h, 1, code))
+
+    def arithmetic(self):
+        """The mode this model resolved to: "fma", "reference" or "strict"."""
+        m = C.c_int(0)
+        _lib.check(self._lib.dcrf_get_arithmetic(self._h, C.byref(m)))
+        return ("fma", "reference", "strict")[m.value]
 
     def set_exact_arithmetic(self, on=True):
         """Round-1 name: True -> "strict", False -> "fma"."""
@@ -379,8 +387,7 @@ class DenseCRFBatch(_Model):
         return x
 
     def setUnaryEnergy(self, u, f=None):
-        u = self._flat(u, np.float32, self._npix * self._L, "unary")
-        ptr, dev, _, keep = _buffer(u, np.float32, "unary")
+        ptr, dev, keep = self._input(u, np.float32, self._npix * self._L, "unary")
         self._pre_device_input(dev)
         _lib.check(self._lib.dcrf_set_unary(self._h, ptr, dev))
         if dev:
@@ -390,36 +397,66 @@ class DenseCRFBatch(_Model):
     def addPairwiseEnergy(self, *a, **k):
         raise NotImplementedError("addPairwiseEnergy is single-image only")
 
+    def _input(self, x, np_dtype, per_image_elems, what):
+        """Host (ndarray / list of arrays) or device (torch CUDA tensor / list of them) input ->
+        (pointer, on_device, keepalive).  Host data is made contiguous and cast; device tensors must
+        already have the right dtype and be contiguous (no hidden device copies)."""
+        total = int(sum(per_image_elems))
+        if isinstance(x, (list, tuple)) and len(x) and _is_torch(x[0]):
+            import torch
+
+            if len(x) != self._B:
+                raise ValueError("%s: expected %d images, got %d" % (what, self._B, len(x)))
+            x = torch.cat([t.reshape(-1) for t in x])
+        if _is_torch(x):
+            if x.numel() != total:
+                raise ValueError("%s: expected %d elements in total, got %d" % (what, total, x.numel()))
+            ptr, dev, _, keep = _buffer(x, np_dtype, what)
+            return ptr, dev, keep
+        x = self._flat(x, np_dtype, per_image_elems, what)
+        a = np.ascontiguousarray(x, dtype=np_dtype).reshape(-1)
+        return a.ctypes.data, 0, a
+
     # -- unary construction on the GPU (the NumPy glue of the reference's wrappers) --
     def setUnaryFromSoftmax(self, probs, scale=None, clip=1e-5):
         """`setUnaryEnergy(unary_from_softmax(probs, scale, clip))` without the host-side log:
-        probs = per-image (L, ...) class probabilities (list, or one concatenated array), float64
-        or float32 (03c_hsn/utilities.py:431-432)."""
-        if isinstance(probs, (list, tuple)):
-            dt = np.float64 if np.asarray(probs[0]).dtype == np.float64 else np.float32
-        else:
-            dt = np.float64 if probs.dtype == np.float64 else np.float32
-        x = self._flat(probs, dt, self._npix * self._L, "probs")
-        a = np.ascontiguousarray(x, dtype=dt).reshape(-1)
+        probs = per-image (L, ...) class probabilities (list, one concatenated array, or a torch CUDA
+        tensor that then never leaves the GPU), float64 or float32 (03c_hsn/utilities.py:431-432)."""
+        first = probs[0] if isinstance(probs, (list, tuple)) else probs
+        is64 = str(first.dtype).endswith("float64")
+        dt = np.float64 if is64 else np.float32
         if scale is not None and not 0 < scale <= 1:
             raise AssertionError("`scale` needs to be in (0,1]")
+        ptr, dev, keep = self._input(probs, dt, self._npix * self._L, "probs")
+        self._pre_device_input(dev)
         _lib.check(self._lib.dcrf_set_unary_from_probs(
-            self._h, a.ctypes.data, 1 if dt == np.float64 else 0, 1.0 if scale is None else float(scale),
-            0.0 if clip is None else float(clip), 0 if clip is None else 1, 0))
+            self._h, ptr, 1 if is64 else 0, 1.0 if scale is None else float(scale),
+            0.0 if clip is None else float(clip), 0 if clip is None else 1, dev))
+        if dev:
+            self._sync_unless_async()
+        del keep
 
     def setUnaryFromLogits(self, feats, use_log=True):
-        """Unary of SEC/DSRG's crf_inference: feats = per-image (H, W, L) float32 feature maps;
-        U = -log softmax_L(feat) (use_log) or -log(feat)."""
-        x = self._flat(feats, np.float32, self._npix * self._L, "feats")
-        a = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
-        _lib.check(self._lib.dcrf_set_unary_from_logits(self._h, a.ctypes.data, 1 if use_log else 0, 0))
+        """Unary of SEC/DSRG's crf_inference (use_log=True): feats = per-image (H, W, L) float32
+        feature maps (host arrays or a CUDA tensor); U = -log softmax_L(feat)."""
+        if not use_log:
+            # [EXT] lib/crf.py is not in the reference tree and no call site passes use_log=False
+            # (SEC.py:275, DSRG.py:328, model.py:689,693 all use the default): not guessed here
+            raise NotImplementedError("crf_inference(use_log=False) is not exercised by the reference")
+        ptr, dev, keep = self._input(feats, np.float32, self._npix * self._L, "feats")
+        self._pre_device_input(dev)
+        _lib.check(self._lib.dcrf_set_unary_from_logits(self._h, ptr, 1, dev))
+        if dev:
+            self._sync_unless_async()
+        del keep
 
     def setUnaryFromLabels(self, labels, gt_prob, zero_unsure=True):
-        """`setUnaryEnergy(unary_from_labels(labels, L, gt_prob, zero_unsure))` on the GPU."""
-        x = self._flat(labels, np.int32, self._npix, "labels")
-        a = np.ascontiguousarray(x, dtype=np.int32).reshape(-1)
-        _lib.check(self._lib.dcrf_set_unary_from_labels(self._h, a.ctypes.data, float(gt_prob),
-                                                        1 if zero_unsure else 0, 0))
+        """`setUnaryEnergy(unary_from_labels(labels, L, gt_prob, zero_unsure))` on the GPU; labels:
+        int32 (host arrays of any integer type are cast, CUDA tensors must be int32)."""
+        ptr, dev, keep = self._input(labels, np.int32, self._npix, "labels")
+        self._pre_device_input(dev)
+        _lib.check(self._lib.dcrf_set_unary_from_labels(self._h, ptr, float(gt_prob), 1 if zero_unsure else 0, dev))
+        del keep
 
     def addPairwiseGaussian(self, sxy, compat, kernel=DIAG_KERNEL, normalization=NORMALIZE_SYMMETRIC):
         sx, sy = _pair(sxy, 2, "sxy")
@@ -431,8 +468,7 @@ class DenseCRFBatch(_Model):
                              normalization=NORMALIZE_SYMMETRIC):
         sx, sy = _pair(sxy, 2, "sxy")
         sr, sg, sb = _pair(srgb, 3, "srgb")
-        rgbim = self._flat(rgbim, np.uint8, self._npix * 3, "rgbim")
-        ptr, dev, _, keep = _buffer(rgbim, np.uint8, "rgbim")
+        ptr, dev, keep = self._input(rgbim, np.uint8, self._npix * 3, "rgbim")
         kind, c = _compat(compat, self._L)
         self._pre_device_input(dev)
         _lib.check(self._lib.dcrf_add_pairwise_bilateral(self._h, sx, sy, sr, sg, sb, ptr, dev, kind,
@@ -467,13 +503,28 @@ class DenseCRFBatch(_Model):
         self._sync_unless_async()
         return out
 
-    def map(self, niter, out=None):
-        """-> list of (H_b, W_b) int32 label maps (views of `out` when given)."""
-        flat = np.empty(self._Ntot, np.int32) if out is None else out
-        assert flat.dtype == np.int32 and flat.size == self._Ntot and flat.flags.c_contiguous
+    def map(self, niter, out=None, dtype=np.int32):
+        """-> list of (H_b, W_b) label maps (views of `out` when given), int32 or uint8 (`dtype`, or
+        the dtype of `out`): uint8 is what leaves the GPU cheapest."""
+        flat = np.empty(self._Ntot, dtype) if out is None else out
+        assert flat.dtype in (np.int32, np.uint8) and flat.size == self._Ntot and flat.flags.c_contiguous
         flat = flat.reshape(-1)
-        _lib.check(self._lib.dcrf_map(self._h, int(niter), flat.ctypes.data, 0))
+        fn = self._lib.dcrf_map if flat.dtype == np.int32 else self._lib.dcrf_map_u8
+        _lib.check(fn(self._h, int(niter), flat.ctypes.data, 0))
         return self._split(flat, 1, lambda b: (self._sizes[b][1], self._sizes[b][0]))
+
+    def map_device(self, niter, out=None, dtype=None):
+        """inference + argmax into a CUDA tensor of Ntot labels (int32, or uint8 when `out` / `dtype` say so)."""
+        import torch
+
+        if out is None:
+            out = torch.empty((self._Ntot,), dtype=dtype or torch.int32, device="cuda:%d" % self._dev_index())
+        assert out.is_cuda and out.is_contiguous() and out.numel() == self._Ntot
+        assert out.dtype in (torch.int32, torch.uint8)
+        fn = self._lib.dcrf_map if out.dtype == torch.int32 else self._lib.dcrf_map_u8
+        _lib.check(fn(self._h, int(niter), out.data_ptr(), 1))
+        self._sync_unless_async()
+        return out
 
     # -- split form of inference()/map(): iterate now, download later (pipeline.py) --
     def run(self, niter):
@@ -511,12 +562,13 @@ class DenseCRFBatch(_Model):
         self._sync_unless_async()
         return out
 
-    def labels(self, out=None):
-        """Download argmax of the running Q -> list of (H_b, W_b) int32 label maps."""
-        flat = np.empty(self._Ntot, np.int32) if out is None else out
-        assert flat.dtype == np.int32 and flat.size == self._Ntot and flat.flags.c_contiguous
+    def labels(self, out=None, dtype=np.int32):
+        """Download argmax of the running Q -> list of (H_b, W_b) int32 / uint8 label maps."""
+        flat = np.empty(self._Ntot, dtype) if out is None else out
+        assert flat.dtype in (np.int32, np.uint8) and flat.size == self._Ntot and flat.flags.c_contiguous
         flat = flat.reshape(-1)
-        _lib.check(self._lib.dcrf_get_labels(self._h, flat.ctypes.data, 0))
+        fn = self._lib.dcrf_get_labels if flat.dtype == np.int32 else self._lib.dcrf_get_labels_u8
+        _lib.check(fn(self._h, flat.ctypes.data, 0))
         return self._split(flat, 1, lambda b: (self._sizes[b][1], self._sizes[b][0]))
 
     def startInference(self):

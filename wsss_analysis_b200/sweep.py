@@ -69,3 +69,49 @@ def run_sweep(items, n_labels, rank=0, world_size=1, batch=16, crf=VOC_CRF, devi
     conf = acc.result()
     return dict(confusion=conf, miou_irn=iou_irn(conf)[1], miou_sec=iou_sec(conf)[1], images=len(mine),
                 seconds=seconds, bad_predictions=acc.bad_predictions())
+
+
+def run_sweep_device(n_items, n_labels, rank=0, world_size=1, batch=32, crf=VOC_CRF, device=0, all_reduce=True,
+                     verify=True, seed=0):
+    """The same sweep with inputs synthesised on the GPU (`synthetic.torch_sweep_item`) and handed over
+    as device tensors: unaries, images, label maps and the confusion matrix never touch the host.
+    Image i goes to rank i mod world_size (`split_dataset` striding, cam_to_ir_label.py:114-117).
+    verify: this rank's (C+1, C) matrix is also computed with np.bincount from the downloaded label
+    maps and must match bit for bit (raises otherwise).
+    Returns dict(confusion (all-reduced), miou_irn, miou_sec, images, pixels, seconds, verified)."""
+    import torch
+
+    dev = torch.device("cuda", int(device))
+    mine = shard_indices(n_items, rank, world_size)
+    acc = ConfusionAccumulator(n_labels, device=device)
+    ref = np.zeros((n_labels + 1, n_labels), np.int64)
+    seconds, pixels = 0.0, 0
+    with torch.cuda.device(dev):
+        for b0 in range(0, len(mine), batch):
+            items = [synthetic.torch_sweep_item(i, n_labels, dev, seed) for i in mine[b0:b0 + batch]]
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            sizes = [(int(im.shape[1]), int(im.shape[0])) for im, _, _ in items]
+            d = DenseCRFBatch(sizes, n_labels, device=device)
+            d.setUnaryEnergy([u for _, u, _ in items])
+            d.addPairwiseGaussian(sxy=crf["g_sxy"], compat=crf["g_compat"])
+            d.addPairwiseBilateral(sxy=crf["bi_sxy"], srgb=crf["bi_srgb"], rgbim=[im for im, _, _ in items],
+                                   compat=crf["bi_compat"])
+            labels = d.map_device(crf["iterations"])          # int32, concatenated, stays on the GPU
+            d.close()
+            gt = torch.cat([g.reshape(-1) for _, _, g in items])
+            acc.update(gt, labels)
+            acc.synchronize()
+            seconds += time.perf_counter() - t0
+            pixels += int(gt.numel())
+            if verify:
+                g_h, p_h = gt.cpu().numpy().astype(np.int64), labels.cpu().numpy().astype(np.int64)
+                row = np.where((g_h >= 0) & (g_h < n_labels), g_h, n_labels)
+                ref += np.bincount(row * n_labels + p_h, minlength=(n_labels + 1) * n_labels).reshape(n_labels + 1, n_labels)
+    if verify and not np.array_equal(acc.result(), ref):
+        raise AssertionError("GPU confusion matrix differs from np.bincount on rank %d" % rank)
+    if all_reduce:
+        acc.all_reduce()
+    conf = acc.result()
+    return dict(confusion=conf, miou_irn=iou_irn(conf)[1], miou_sec=iou_sec(conf)[1], images=len(mine),
+                pixels=pixels, seconds=seconds, verified=bool(verify), bad_predictions=acc.bad_predictions())

@@ -97,3 +97,41 @@ def gt_map(H, W, C, seed=0, ignore=255, border=4):
     gt[:, :border] = ignore
     gt[:, -border:] = ignore
     return gt
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU-side generation for the 1449-image sweep (BASELINE config 5): the NumPy generators above cost
+# ~0.1 s per VOC-sized item, the sweep itself ~1 ms.  Every item is a pure function of (i, seed) --
+# independent of rank, world size and batch composition -- so any sharding sees the same inputs.
+# ------------------------------------------------------------------------------------------------
+def torch_sweep_item(i, n_labels, device, seed=0):
+    """Item i of the synthetic VOC-val-shaped list on `device`:
+    (image uint8 (H, W, 3), unary float32 (L, H*W), gt int32 (H, W) with a 255 'ignore' border)."""
+    import torch
+    import torch.nn.functional as F
+
+    w, h = voc_like_size(i, seed)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1_000_003 * (seed + 1) + i)
+    # natural-like image: smooth colour field (bicubic upsample of a coarse uniform grid) + N(0, 8) noise
+    gh, gw = h // 32 + 2, w // 32 + 2
+    grid = torch.rand((1, 3, gh, gw), generator=gen, device=device) * 255.0
+    img = F.interpolate(grid, size=(h, w), mode="bicubic", align_corners=False)[0]
+    img = img + torch.randn((3, h, w), generator=gen, device=device) * 8.0
+    img = img.clamp(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous()
+    # ground truth: argmax of per-class smooth fields on a 1/8 grid, replicated; 255 border
+    hc, wc = (h + 7) // 8, (w + 7) // 8
+    z = torch.randn((1, n_labels, hc // 4 + 2, wc // 4 + 2), generator=gen, device=device)
+    z = F.interpolate(z, size=(hc, wc), mode="bilinear", align_corners=False)[0]
+    gt = z.argmax(0).repeat_interleave(8, 0).repeat_interleave(8, 1)[:h, :w].to(torch.int32).contiguous()
+    lab = gt.reshape(-1).long()
+    border = 4
+    gt[:border] = 255
+    gt[-border:] = 255
+    gt[:, :border] = 255
+    gt[:, -border:] = 255
+    # unary: noisy evidence for the GT label, -log softmax
+    e = torch.randn((n_labels, h * w), generator=gen, device=device) * 1.5
+    e[lab, torch.arange(h * w, device=device)] += 2.0
+    unary = (-torch.log_softmax(e, dim=0)).contiguous()
+    return img, unary, gt

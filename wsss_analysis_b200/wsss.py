@@ -95,17 +95,18 @@ def dcrf_process(probs, images, config, device=None):
     return out
 
 
-def _unary_from_featmap(feat, use_log):
-    """[EXT] unary of SEC's crf_inference: softmax over the class axis then -log (use_log=True), or
-    -log of the given probabilities; returned as C-contiguous (C, H*W) float32."""
+def _unary_from_featmap(feat, use_log=True):
+    """[EXT] unary of SEC's crf_inference(use_log=True): softmax over the class axis then -log,
+    returned as C-contiguous (C, H*W) float32.  (Host form kept for callers / tests; the batched path
+    computes it on the GPU.)  use_log=False is exercised by no call site of the reference and the
+    wrapper's source is not in its tree, so that branch is not guessed."""
+    if not use_log:
+        raise NotImplementedError("crf_inference(use_log=False) is not exercised by the reference")
     feat = np.asarray(feat, dtype=np.float32)
     C_ = feat.shape[-1]
-    if use_log:
-        feat = np.exp(feat - np.max(feat, axis=2, keepdims=True))
-        feat /= np.sum(feat, axis=2, keepdims=True)
-        unary = -np.log(feat)
-    else:
-        unary = -np.log(feat)
+    feat = np.exp(feat - np.max(feat, axis=2, keepdims=True))
+    feat /= np.sum(feat, axis=2, keepdims=True)
+    unary = -np.log(feat)
     unary = np.reshape(unary, (-1, C_))
     unary = np.swapaxes(unary, 0, 1)
     return np.copy(unary, order="C").astype(np.float32, copy=False)
