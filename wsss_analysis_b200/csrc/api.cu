@@ -10,8 +10,9 @@
 
 #include <algorithm>
 #include <memory>
+#include <map>
 #include <mutex>
-#include <unordered_map>
+#include <utility>
 
 #include "common.cuh"
 
@@ -23,39 +24,102 @@ thread_local Profiler *t_prof = nullptr;
 void set_error(const std::string &msg) { t_error = msg; }
 
 namespace {
-// Persistent per-thread streams (main + side) per device: a handle created without a caller stream
-// runs on its creating thread's stream, so consecutive handles of a thread reuse the thread's pool
-// blocks in plain stream order and no stream is created / destroyed per image.
-struct ThreadStreams {
-    cudaStream_t main[64] = {};
-    cudaStream_t side[64][kMaxPairwise - 1] = {};
-    cudaStream_t upload[64] = {};
-    ~ThreadStreams() {
-        for (int d = 0; d < 64; d++) {
-            if (main[d]) cudaStreamDestroy(main[d]);
-            if (upload[d]) cudaStreamDestroy(upload[d]);
-            for (auto s : side[d])
-                if (s) cudaStreamDestroy(s);
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) DCRF_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// The streams that accompany one primary stream: side streams for the concurrent pairwise filters
+// and an upload stream, plus the primary itself when the library created it.  Reference counted --
+// every handle that runs on the primary holds a reference, so a handle may outlive the thread that
+// created it (a Python object collected or closed from another thread, a ThreadPool worker that
+// exits): the streams and their memory pools go away with the LAST holder, never under a live handle.
+struct StreamSet {
+    int dev = 0;
+    cudaStream_t primary = nullptr;
+    bool owns_primary = false;
+    std::mutex mu;
+    cudaStream_t side[kMaxPairwise - 1] = {};
+    cudaStream_t upload = nullptr;
+    cudaStream_t get_side(int k) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!side[k]) {
+            DeviceGuard g(dev);
+            DCRF_CUDA(cudaStreamCreateWithFlags(&side[k], cudaStreamNonBlocking));
+        }
+        return side[k];
+    }
+    cudaStream_t get_upload() {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!upload) {
+            DeviceGuard g(dev);
+            DCRF_CUDA(cudaStreamCreateWithFlags(&upload, cudaStreamNonBlocking));
+        }
+        return upload;
+    }
+    ~StreamSet() {
+        try {
+            DeviceGuard g(dev);
+            for (auto st : side)
+                if (st) {
+                    cudaStreamSynchronize(st);
+                    stream_pool_release(st);
+                    cudaStreamDestroy(st);
+                }
+            if (upload) {
+                cudaStreamSynchronize(upload);
+                stream_pool_release(upload);
+                cudaStreamDestroy(upload);
+            }
+            if (owns_primary && primary) {
+                cudaStreamSynchronize(primary);
+                stream_pool_release(primary);
+                cudaStreamDestroy(primary);
+            }
+        } catch (...) {
         }
     }
 };
-thread_local ThreadStreams t_streams;
-}  // namespace
 
-static cudaStream_t thread_main_stream(int dev) {
-    if (!t_streams.main[dev]) DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.main[dev], cudaStreamNonBlocking));
-    return t_streams.main[dev];
+std::shared_ptr<StreamSet> new_owned_set(int dev) {
+    auto set = std::make_shared<StreamSet>();
+    set->dev = dev;
+    set->owns_primary = true;
+    DCRF_CUDA(cudaStreamCreateWithFlags(&set->primary, cudaStreamNonBlocking));
+    return set;
 }
-static cudaStream_t thread_upload_stream(int dev) {
-    if (!t_streams.upload[dev])
-        DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.upload[dev], cudaStreamNonBlocking));
-    return t_streams.upload[dev];
+
+// the calling thread's persistent stream set per device: a handle created without a caller stream
+// runs on it, so consecutive handles of a thread reuse the thread's pool blocks in plain stream order
+// and no stream is created / destroyed per image
+thread_local std::shared_ptr<StreamSet> t_sets[64];
+std::shared_ptr<StreamSet> thread_set(int dev) {
+    DCRF_REQUIRE(dev >= 0 && dev < 64, DCRF_EINVAL, "device index out of range");
+    if (!t_sets[dev]) t_sets[dev] = new_owned_set(dev);
+    return t_sets[dev];
 }
-static cudaStream_t thread_side_stream(int dev, int k) {
-    if (!t_streams.side[dev][k])
-        DCRF_CUDA(cudaStreamCreateWithFlags(&t_streams.side[dev][k], cudaStreamNonBlocking));
-    return t_streams.side[dev][k];
+
+// sets of caller-provided primaries (torch streams, dcrf_stream_create): kept in a registry so that
+// handle after handle on the same stream reuses the same side / upload streams
+std::mutex g_sets_mu;
+std::map<std::pair<int, cudaStream_t>, std::shared_ptr<StreamSet>> g_sets;
+std::shared_ptr<StreamSet> caller_set(int dev, cudaStream_t primary) {
+    std::lock_guard<std::mutex> lock(g_sets_mu);
+    auto &slot = g_sets[std::make_pair(dev, primary)];
+    if (!slot) {
+        slot = std::make_shared<StreamSet>();
+        slot->dev = dev;
+        slot->primary = primary;
+    }
+    return slot;
 }
+}  // namespace
 
 double trace_now() {
     static const bool on = getenv("DCRF_TRACE") != nullptr;
@@ -71,14 +135,14 @@ void trace_slow(const char *what, double t0, size_t bytes) {
 }
 
 static std::mutex g_pool_mu;
-static std::unordered_map<cudaStream_t, cudaMemPool_t> g_pools;
+static std::map<std::pair<int, cudaStream_t>, cudaMemPool_t> g_pools;  // key: (device, stream)
 
 cudaMemPool_t stream_pool(cudaStream_t stream) {
-    std::lock_guard<std::mutex> lock(g_pool_mu);
-    auto it = g_pools.find(stream);
-    if (it != g_pools.end()) return it->second;
     int dev = 0;
     DCRF_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    auto it = g_pools.find(std::make_pair(dev, stream));
+    if (it != g_pools.end()) return it->second;
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -88,7 +152,7 @@ cudaMemPool_t stream_pool(cudaStream_t stream) {
     DCRF_CUDA(cudaMemPoolCreate(&pool, &props));
     uint64_t thr = UINT64_MAX;  // keep freed blocks cached: every image needs fresh lattice buffers
     DCRF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    g_pools[stream] = pool;
+    g_pools[std::make_pair(dev, stream)] = pool;
     return pool;
 }
 
@@ -97,9 +161,12 @@ static void trim_all_pools() {
     for (auto &kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
 }
 
+// (current device = the stream's device)
 void stream_pool_release(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
     std::lock_guard<std::mutex> lock(g_pool_mu);
-    auto it = g_pools.find(stream);
+    auto it = g_pools.find(std::make_pair(dev, stream));
     if (it == g_pools.end()) return;
     cudaMemPoolDestroy(it->second);
     g_pools.erase(it);
@@ -122,8 +189,8 @@ using namespace dcrf;
 
 struct dcrf_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
+    cudaStream_t stream = nullptr;          // = streams->primary
+    std::shared_ptr<StreamSet> streams;     // keeps the primary's side / upload streams (and pools) alive
     int L = 0, Lp = 0;
     bool has_geom = false;  // 2-D image geometry available (Gaussian / bilateral features)
     BatchGeom geom;
@@ -137,7 +204,6 @@ struct dcrf_handle {
     Profiler prof;
     // side streams: the filters of all pairwise terms but the last run concurrently with the last
     // one (the small, latency-bound Gaussian lattice hides behind the bandwidth-bound bilateral one)
-    cudaStream_t side[kMaxPairwise - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxPairwise - 1] = {};
     // async-host mode: the unary upload (H2D + layout change) runs on the thread's upload stream so
     // that the lattice builds enqueued next on `stream` overlap it; joined before the unary is read
@@ -148,16 +214,6 @@ struct dcrf_handle {
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) DCRF_CUDA(cudaSetDevice(dev));
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 struct ProfGuard {
     explicit ProfGuard(dcrf_handle *h) { t_prof = &h->prof; }
     ~ProfGuard() { t_prof = nullptr; }
@@ -236,14 +292,10 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     std::unique_ptr<dcrf_handle> h(new dcrf_handle());
     h->device = device;
     DeviceGuard guard(device);
-    if (stream == DCRF_STREAM_DEDICATED) {
-        DCRF_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        h->own_stream = true;
-    } else if (stream) {
-        h->stream = (cudaStream_t)stream;
-    } else {
-        h->stream = thread_main_stream(device);  // persistent, owned by the calling thread
-    }
+    if (stream == DCRF_STREAM_DEDICATED) h->streams = new_owned_set(device);  // lives and dies with this handle
+    else if (stream) h->streams = caller_set(device, (cudaStream_t)stream);
+    else h->streams = thread_set(device);  // persistent; shared with the calling thread's other handles
+    h->stream = h->streams->primary;
     h->L = L;
     h->Lp = ((L + 3) / 4) * 4;
     h->has_geom = has_geom;
@@ -442,17 +494,15 @@ void step_inference(dcrf_handle *h) {
         if (!h->ev_fork) {
             const double t0 = trace_now();
             DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-            for (int k = 0; k < kMaxPairwise - 1; k++) {
-                h->side[k] = thread_side_stream(h->device, k);
+            for (int k = 0; k < kMaxPairwise - 1; k++)
                 DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming));
-            }
             trace_slow("side stream/event creation", t0, 0);
         }
         DCRF_CUDA(cudaEventRecord(h->ev_fork, h->stream));
     }
     for (int k = 0; k < n; k++) {
         Pairwise &p = *h->pw[k];
-        cudaStream_t st = (overlap && k < n - 1) ? h->side[k] : h->stream;
+        cudaStream_t st = (overlap && k < n - 1) ? h->streams->get_side(k) : h->stream;
         if (st != h->stream) DCRF_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0));
         const float *blurred =
             filter_to_lattice(h, p, h->Q.p, h->Lp, pre_norm(p.ntype), seq, p.valA.p, p.valB.p, fast, st);
@@ -556,11 +606,7 @@ void dcrf_destroy(dcrf_t *h) {
             cudaEventDestroy(h->ev_fork);
             for (int k = 0; k < kMaxPairwise - 1; k++) cudaEventDestroy(h->ev_join[k]);
         }
-        if (h->own_stream) {
-            cudaStreamSynchronize(h->stream);
-            stream_pool_release(h->stream);
-            cudaStreamDestroy(h->stream);
-        }
+        h->streams.reset();  // the last holder destroys the set's streams and their pools
         trace_slow("dcrf_destroy", t0, 0);
     } catch (...) {
     }
@@ -583,18 +629,31 @@ int dcrf_stream_create(int device, void **stream_out) {
         if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
         DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
         DeviceGuard guard(device);
-        cudaStream_t s;
-        DCRF_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        *stream_out = (void *)s;
+        auto set = new_owned_set(device);
+        {
+            std::lock_guard<std::mutex> lock(g_sets_mu);
+            g_sets[std::make_pair(device, set->primary)] = set;
+        }
+        *stream_out = (void *)set->primary;
     });
 }
 
 int dcrf_stream_destroy(void *stream) {
     return guarded([&] {
         DCRF_REQUIRE(stream, DCRF_EINVAL, "NULL stream");
-        DCRF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-        stream_pool_release((cudaStream_t)stream);
-        DCRF_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+        // drop the registry's reference: the stream, its side streams and their pools are destroyed now,
+        // or with the last handle still running on it
+        std::shared_ptr<StreamSet> set;
+        {
+            std::lock_guard<std::mutex> lock(g_sets_mu);
+            for (auto it = g_sets.begin(); it != g_sets.end(); ++it)
+                if (it->first.second == (cudaStream_t)stream && it->second->owns_primary) {
+                    set = it->second;
+                    g_sets.erase(it);
+                    break;
+                }
+        }
+        DCRF_REQUIRE(set != nullptr, DCRF_EINVAL, "not a stream created by dcrf_stream_create");
     });
 }
 
@@ -642,7 +701,7 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
         join_upload(h);
         if (!on_device && h->async_host) {
             // H2D + layout change on the upload stream; `stream` goes on (lattice builds) meanwhile
-            const cudaStream_t up = thread_upload_stream(h->device);
+            const cudaStream_t up = h->streams->get_upload();
             if (!h->ev_upload_begin) {
                 DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_upload_begin, cudaEventDisableTiming));
                 DCRF_CUDA(cudaEventCreateWithFlags(&h->ev_upload_end, cudaEventDisableTiming));
@@ -1039,7 +1098,8 @@ int dcrf_expf_ref(const float *x, float *y, int64_t n, int device) {
         if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
         DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
         DeviceGuard guard(device);
-        cudaStream_t s = thread_main_stream(device);
+        const std::shared_ptr<StreamSet> set = thread_set(device);
+        cudaStream_t s = set->primary;
         DevBuf<float> dx, dy;
         dx.alloc((size_t)n, s);
         dy.alloc((size_t)n, s);
