@@ -69,6 +69,8 @@ SWEEP_IMAGES, SWEEP_LABELS, SWEEP_BATCH = 1449, 21, 32  # configs[4]; 03b_irn/vo
 # measured LSU row-gather ceiling (tools/micro/bulk_gather.cu, profiles/r1_micro_gather.txt; the TMA
 # gather4 path tops out at 127 G rows/s: profiles/r2_micro_gather4.txt)
 GATHER_CEILING_GROWS = 106.7
+# lattice-construction phases timed by the library (include/dcrf_b200.h, DCRF_K_BUILD_*)
+BUILD_PHASES = ("point", "hash", "number", "neigh", "sort", "csr", "norm", "repl")
 
 
 def npix(cfg):
@@ -306,6 +308,7 @@ class Runner(object):
         if L * self.N * 4 <= 126e6:   # inputs fit L2: flush it between timed steps
             self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
         self.prof = {"splat": {}, "blur": {}, "slice": {}}
+        self.build_prof = OrderedDict()   # (phase, d) -> total ms over the profiled steps
         self.lattice_M = {}
         self.arith = None
 
@@ -345,6 +348,11 @@ class Runner(object):
                     a = self.prof[cls].setdefault(tag, [0.0, 0])
                     a[0] += ms
                     a[1] += n
+            for cid, phase in enumerate(BUILD_PHASES, start=3):
+                for tag in (2, 5):
+                    ms, n = crf.profile_read(cid, tag)
+                    if n:
+                        self.build_prof[(phase, tag)] = self.build_prof.get((phase, tag), 0.0) + ms
         crf.close()
 
     def timed(self, steps, profile):
@@ -450,6 +458,7 @@ class Runner(object):
             "arithmetic": self.arith,
             "lattice": {"pixels": N, "labels": L, "vertices": {("d%d" % d): M for d, M in lattices}},
             "build_ms_per_step": r["build_ms"] / steps, "build_share": r["build_share"],
+            "build_phases_ms_per_step": {"%s_d%d" % k: round(v / steps, 4) for k, v in self.build_prof.items()},
             "iteration_only": {"value": iter_only, "unit": UNIT + " per GPU", "ms_per_step": kernel_ms / steps},
             "step_roofline": {
                 "bytes_per_pixel_iteration": b_iter / N, "ceiling": ceiling, "unit": UNIT + " per GPU",
@@ -648,6 +657,7 @@ def run_ours(args):
         "arithmetic": obj["arithmetic"],
         "images_per_s": obj["images_per_s"],
         "lattice": obj["lattice"], "build_ms_per_step": obj["build_ms_per_step"],
+        "build_phases_ms_per_step": obj["build_phases_ms_per_step"],
         # SURVEY.md 8d asks for both figures: `value` includes the per-image lattice build; this one
         # counts the mean-field iteration kernels only (rank 0's serialised per-kernel event times)
         "iteration_only": obj["iteration_only"],

@@ -58,6 +58,10 @@ const char *dcrf_last_error(void);
 const char *dcrf_version(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t dcrf_launch_count(void);
+/* bytes this library has copied host -> device and device -> host in the calling process (payload and
+ * metadata alike).  Calls that are given device pointers (on_device = 1) move only a few hundred bytes
+ * of batch geometry; tests/test_gpu_wsss.py asserts it. */
+void dcrf_copy_count(int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* ---- construction --------------------------------------------------------------------------- */
 
@@ -221,7 +225,15 @@ int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int 
 /* ---- measurement hooks (bench.py's roofline object) ------------------------------------------ */
 
 /* Kernel classes timed with CUDA events recorded on the handle's stream around every launch. */
-enum { DCRF_K_SPLAT = 0, DCRF_K_BLUR = 1, DCRF_K_SLICE = 2 };
+enum {
+    DCRF_K_SPLAT = 0, DCRF_K_BLUR = 1, DCRF_K_SLICE = 2,
+    /* lattice construction phases (tag = d): point = elevate / round / rank / barycentric; hash = key
+     * insertion; number = first-occurrence flags + scan + offsets; neigh = compact table + neighbour
+     * look-ups; sort = radix sort of the entries by vertex; csr = CSR rows + packed entry tables;
+     * norm = kernel normalisation (filter of all-ones); repl = replication of a position-only lattice */
+    DCRF_K_BUILD_POINT = 3, DCRF_K_BUILD_HASH = 4, DCRF_K_BUILD_NUMBER = 5, DCRF_K_BUILD_NEIGH = 6,
+    DCRF_K_BUILD_SORT = 7, DCRF_K_BUILD_CSR = 8, DCRF_K_BUILD_NORM = 9, DCRF_K_BUILD_REPL = 10
+};
 int dcrf_profile_enable(dcrf_t *h, int enable);
 /* Synchronises the stream, then sums the recorded launches of `kernel_class` whose tag equals `tag`
  * (tag = lattice dimension d for splat / blur, number of fused pairwise terms for slice; -1 = any).

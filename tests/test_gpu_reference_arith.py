@@ -142,7 +142,7 @@ def test_adp_1088_morph_29_labels_vs_oracle():
     L = 29
     img = S.histo_image(H, W, 2, n_blobs=25)
     U = S.random_unary(L, W * H, 2)
-    o, (g, ga) = _models(W, H, L, 1, 20, 10, 40, 50, img, U, modes=("reference", "auto"))
+    o, (g, ga, gs) = _models(W, H, L, 1, 20, 10, 40, 50, img, U, modes=("reference", "auto", "strict"))
     for k in range(2):
         eo, eg = o.lattice(k), g.lattice_export(k)
         assert eo.M == eg["M"] and np.array_equal(eo.offsets, eg["offsets"])
@@ -151,9 +151,10 @@ def test_adp_1088_morph_29_labels_vs_oracle():
     assert np.abs(Qo - Qg).max() <= 1e-4 and (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999
     assert ga.arithmetic() == "fma"
     assert np.abs(Qo - Qa).max() <= 1e-4 and (Qo.argmax(0) == Qa.argmax(0)).mean() >= 0.999
-    # histology backgrounds are near-flat: rows longer than 256 entries exist, whose tails the default
-    # mode sums by a tree; everything else is bit-identical
-    assert (_bits(Qo) == _bits(Qg)).mean() >= 0.99
+    # histology backgrounds are near-flat: splat rows longer than 256 entries are common here, and
+    # "reference" sums their tails by a tree (rounding-level differences that the blur spreads);
+    # "strict" sums every row in the oracle's order
+    assert np.array_equal(_bits(Qo), _bits(gs.inference(5)))
 
 
 def test_deepglobe_2448_vs_oracle():
@@ -164,11 +165,11 @@ def test_deepglobe_2448_vs_oracle():
     L = 6
     img = S.natural_image(H, W, 3)
     U = S.random_unary(L, W * H, 3)
-    o, (g, ga) = _models(W, H, L, 3, 3, 80, 13, 10, img, U, modes=("reference", "auto"))
+    o, (g, ga, gs) = _models(W, H, L, 3, 3, 80, 13, 10, img, U, modes=("reference", "auto", "strict"))
     assert o.lattice(1).M == g.lattice_export(1, with_norm=False)["M"]
     Qo, Qg, Qa = o.inference(10), g.inference(10), ga.inference(10)
     assert np.abs(Qo - Qg).max() <= 1e-4 and (Qo.argmax(0) == Qg.argmax(0)).mean() >= 0.999
-    assert (_bits(Qo) == _bits(Qg)).mean() >= 0.99
+    assert np.array_equal(_bits(Qo), _bits(gs.inference(10)))
     assert ga.arithmetic() == "fma"
     assert np.abs(Qo - Qa).max() <= 1e-4 and (Qo.argmax(0) == Qa.argmax(0)).mean() >= 0.999
 

@@ -335,3 +335,104 @@ def test_crf_inference_label_shares_lattices_between_label_sets():
     for k in range(2):
         for a, b in zip(both[k], sep[k]):
             assert np.array_equal(a, b)
+
+
+def test_wrappers_accept_cuda_tensors_and_move_no_payload_over_pcie():
+    """dcrf_process, crf_inference_batch, sec_crf_layer and
+    crf_inference_label_batch given torch CUDA tensors return CUDA tensors with the same values as
+    the host-array calls, and the library's own H2D / D2H byte counters (dcrf_copy_count) only see
+    batch geometry and vertex counts -- no unaries, images, marginals or label maps."""
+    import torch
+
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200 import wsss
+
+    dev = torch.device("cuda", 0)
+    B, C_, H, W = 3, 7, 40, 56
+    rng = np.random.default_rng(5)
+    images = np.stack([S.natural_image(H, W, 20 + i) for i in range(B)])
+    probs = np.stack([S.blob_probs(C_, H, W, 30 + i, n_active=4) for i in range(B)])
+    feat = rng.standard_normal((B, H, W, C_)).astype(np.float32) * 2
+    labels = rng.integers(0, C_, (B, H, W)).astype(np.int64)
+    cfg = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 80, "bi_srgb": 13, "bi_compat": 10, "iterations": 5}
+    hsn = (1.5, 3, 40, 13, 10, np.float64(5.0))
+    # host-array results first (these do use PCIe)
+    want_proc = wsss.dcrf_process(probs, images, hsn)
+    want_inf = wsss.crf_inference_batch(list(images), cfg, C_, list(feat))
+    want_sec = wsss.sec_crf_layer(feat, images.astype(np.float32), cfg, C_)
+    want_lab = wsss.crf_inference_label_batch(list(images.astype(np.float32)), list(labels), n_labels=C_)
+    t_probs, t_img = torch.from_numpy(probs).to(dev), torch.from_numpy(images).to(dev)
+    t_feat, t_lab = torch.from_numpy(feat).to(dev), torch.from_numpy(labels).to(dev)
+    t_imgf = t_img.to(torch.float32)
+    torch.cuda.synchronize()
+    h0, d0 = G.copy_count()
+    got_proc = wsss.dcrf_process(t_probs, t_img, hsn)
+    got_inf = wsss.crf_inference_batch(t_img, cfg, C_, t_feat)
+    got_sec = wsss.sec_crf_layer(t_feat, t_imgf, cfg, C_)
+    got_lab = wsss.crf_inference_label_batch(t_imgf, t_lab, n_labels=C_)
+    torch.cuda.synchronize()
+    h1, d1 = G.copy_count()
+    payload = min(probs[0].nbytes, images[0].nbytes)
+    assert h1 - h0 < 4096 and d1 - d0 < 4096 and payload > 4096, (h1 - h0, d1 - d0)
+    for t in (got_proc, got_inf, got_sec, got_lab):
+        assert t.is_cuda
+    assert np.array_equal(got_proc.cpu().numpy(), want_proc)
+    assert np.array_equal(got_inf.cpu().numpy(), np.stack(want_inf))
+    assert np.array_equal(got_sec.cpu().numpy(), want_sec)
+    assert np.array_equal(got_lab.cpu().numpy(), np.stack(want_lab))
+
+
+def test_uint8_label_outputs_match_int32():
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+
+    sizes = [(50, 30), (31, 44)]
+    L = 21
+    imgs = [S.natural_image(h, w, i) for i, (w, h) in enumerate(sizes)]
+    Us = [S.random_unary(L, w * h, i) for i, (w, h) in enumerate(sizes)]
+    d = G.DenseCRFBatch(sizes, L)
+    d.setUnaryEnergy(Us)
+    d.addPairwiseGaussian(sxy=3, compat=3)
+    d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=imgs, compat=10)
+    a, b = d.map(4), d.map(4, dtype=np.uint8)
+    for x, y in zip(a, b):
+        assert y.dtype == np.uint8 and x.dtype == np.int32 and np.array_equal(x, y)
+    c = d.labels(dtype=np.uint8)
+    assert all(np.array_equal(x, y) for x, y in zip(a, c))
+    import torch
+
+    t = d.map_device(4, dtype=torch.uint8)
+    assert t.dtype == torch.uint8 and np.array_equal(t.cpu().numpy(), np.concatenate([x.ravel() for x in a]))
+
+
+def test_handle_outlives_its_creating_thread():
+    """a handle created in a worker thread and used / destroyed after that thread
+    has exited must keep working -- it holds a reference on the thread's stream set."""
+    import threading
+
+    from oracle import oracle as O
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+
+    W, H, L = 48, 32, 5
+    img, U = S.natural_image(H, W, 1), S.random_unary(L, W * H, 1)
+    box = {}
+
+    def worker():
+        g = G.DenseCRF2D(W, H, L)
+        g.setUnaryEnergy(U)
+        g.addPairwiseGaussian(sxy=3, compat=3)
+        g.addPairwiseBilateral(sxy=80, srgb=13, rgbim=img, compat=10)
+        box["g"] = g
+
+    for _ in range(3):   # several generations of worker threads: stream handles get recycled
+        th = threading.Thread(target=worker)
+        th.start()
+        th.join()
+        o = O.DenseCRF2D(W, H, L)
+        o.setUnaryEnergy(U)
+        o.addPairwiseGaussian(sxy=3, compat=3)
+        o.addPairwiseBilateral(sxy=80, srgb=13, rgbim=img, compat=10)
+        assert np.abs(box["g"].inference(5) - o.inference(5)).max() <= 1e-4   # side streams created after the thread died
+        box.pop("g").close()

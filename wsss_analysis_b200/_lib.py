@@ -18,6 +18,7 @@ SIGNATURES = {
     "dcrf_last_error": (C.c_char_p, []),
     "dcrf_version": (C.c_char_p, []),
     "dcrf_launch_count": (_i64, []),
+    "dcrf_copy_count": (None, [C.POINTER(_i64), C.POINTER(_i64)]),
     "dcrf_trim_memory": (_i, []),
     "dcrf_stream_create": (_i, [_i, C.POINTER(_vp)]),
     "dcrf_stream_destroy": (_i, [_vp]),

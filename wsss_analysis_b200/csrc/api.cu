@@ -19,6 +19,7 @@
 namespace dcrf {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
 static thread_local std::string t_error;
 thread_local Profiler *t_prof = nullptr;
 void set_error(const std::string &msg) { t_error = msg; }
@@ -318,10 +319,9 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     h->d_w.alloc(B, h->stream);
     h->d_h.alloc(B, h->stream);
     h->d_pix_start.alloc(B + 1, h->stream);
-    DCRF_CUDA(cudaMemcpyAsync(h->d_w.p, g.w.data(), sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
-    DCRF_CUDA(cudaMemcpyAsync(h->d_h.p, g.h.data(), sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
-    DCRF_CUDA(cudaMemcpyAsync(h->d_pix_start.p, ps32.data(), sizeof(int) * (B + 1),
-                              cudaMemcpyHostToDevice, h->stream));
+    DCRF_CUDA(copy_h2d(h->d_w.p, g.w.data(), sizeof(int) * B, h->stream));
+    DCRF_CUDA(copy_h2d(h->d_h.p, g.h.data(), sizeof(int) * B, h->stream));
+    DCRF_CUDA(copy_h2d(h->d_pix_start.p, ps32.data(), sizeof(int) * (B + 1), h->stream));
     DCRF_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope
     g.d_w = h->d_w.p;
     g.d_h = h->d_h.p;
@@ -340,7 +340,7 @@ const T *to_device(dcrf_handle *h, const T *src, size_t count, int on_device, De
     if (on_device) return src;
     stage.alloc(count, h->stream);
     const double t0 = trace_now();
-    DCRF_CUDA(cudaMemcpyAsync(stage.p, src, sizeof(T) * count, cudaMemcpyHostToDevice, h->stream));
+    DCRF_CUDA(copy_h2d(stage.p, src, sizeof(T) * count, h->stream));
     trace_slow("cudaMemcpyAsync H2D (enqueue)", t0, sizeof(T) * count);
     return stage.p;
 }
@@ -397,7 +397,7 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         std::vector<float> c(Lp, 0.f);
         for (int l = 0; l < L; l++) c[l] = compat[l];
         p->compat.alloc(Lp, s);
-        DCRF_CUDA(cudaMemcpyAsync(p->compat.p, c.data(), sizeof(float) * Lp, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(copy_h2d(p->compat.p, c.data(), sizeof(float) * Lp, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     } else {
         // [EXT] MatrixCompatibility stores 0.5 * (m + m^T)
@@ -405,7 +405,7 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         for (int a = 0; a < L; a++)
             for (int b = 0; b < L; b++) c[(size_t)a * Lp + b] = 0.5f * (compat[a * L + b] + compat[b * L + a]);
         p->compat.alloc((size_t)Lp * Lp, s);
-        DCRF_CUDA(cudaMemcpyAsync(p->compat.p, c.data(), sizeof(float) * Lp * Lp, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(copy_h2d(p->compat.p, c.data(), sizeof(float) * Lp * Lp, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     }
     // A lattice whose features depend on the pixel position only (the Gaussian kernel) is the same
@@ -430,10 +430,14 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
     build_lattice(bg, fs, lat, s);
     // A.5: norm = filter(ones) through the value_size = 1 path
     if (ntype != DCRF_NO_NORMALIZATION) {
+        ProfScope prof(DCRF_K_BUILD_NORM, lat.d, s);
         norm.alloc(bg.Ntot, s);
         launch_kernel_norm(lat, bg.Ntot, ntype, norm.p, s);
     }
-    pack_tables(h, lat, ntype, norm.p, s);
+    {
+        ProfScope prof(DCRF_K_BUILD_CSR, lat.d, s);
+        pack_tables(h, lat, ntype, norm.p, s);
+    }
     if (uniform) {
         if (norm.p) p->norm.alloc(Ntot, s);
         launch_replicate_lattice(single, norm.p, h->geom.B, bg.Ntot, p->lat, p->norm.p, s);
@@ -523,7 +527,7 @@ void emit_q(dcrf_handle *h, float *Q_out, int on_device) {
         DevBuf<float> stage;
         stage.alloc(n, h->stream);
         launch_pm_to_ln(h->Q.p, stage.p, h->geom, h->L, h->Lp, h->stream);
-        DCRF_CUDA(cudaMemcpyAsync(Q_out, stage.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+        DCRF_CUDA(copy_d2h(Q_out, stage.p, sizeof(float) * n, h->stream));
         host_sync(h);
     }
 }
@@ -542,7 +546,7 @@ void emit_labels(dcrf_handle *h, T *labels_out, int on_device) {
         DevBuf<T> stage;
         stage.alloc(N, h->stream);
         launch(stage.p);
-        DCRF_CUDA(cudaMemcpyAsync(labels_out, stage.p, sizeof(T) * N, cudaMemcpyDeviceToHost, h->stream));
+        DCRF_CUDA(copy_d2h(labels_out, stage.p, sizeof(T) * N, h->stream));
         host_sync(h);
     }
 }
@@ -565,6 +569,10 @@ extern "C" {
 const char *dcrf_last_error(void) { return t_error.c_str(); }
 const char *dcrf_version(void) { return "dcrf_b200 0.1 sm_100a"; }
 int64_t dcrf_launch_count(void) { return g_launches.load(); }
+void dcrf_copy_count(int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
+    if (d2h_bytes) *d2h_bytes = g_d2h_bytes.load();
+}
 
 int dcrf_create(int w, int h, int n_labels, int device, void *stream, dcrf_t **out) {
     return guarded([&] { create_common(1, &w, &h, true, n_labels, device, stream, out); });
@@ -710,7 +718,7 @@ int dcrf_set_unary(dcrf_t *h, const float *U, int on_device) {
             h->upload_stage.alloc(n, h->stream);
             DCRF_CUDA(cudaEventRecord(h->ev_upload_begin, h->stream));
             DCRF_CUDA(cudaStreamWaitEvent(up, h->ev_upload_begin, 0));
-            DCRF_CUDA(cudaMemcpyAsync(h->upload_stage.p, U, sizeof(float) * n, cudaMemcpyHostToDevice, up));
+            DCRF_CUDA(copy_h2d(h->upload_stage.p, U, sizeof(float) * n, up));
             launch_ln_to_pm(h->upload_stage.p, h->unary.p, h->geom, h->L, h->Lp, up);
             DCRF_CUDA(cudaEventRecord(h->ev_upload_end, up));
             h->upload_pending = true;
@@ -785,7 +793,7 @@ int dcrf_set_unary_from_labels(dcrf_t *h, const int32_t *labels, float gt_prob, 
         launch_unary_from_labels(src, h->unary.p, h->geom.Ntot, h->L, h->Lp, n_energy, p_energy, unsure,
                                  zero_unsure, bad.p, h->stream);
         int h_bad = 0;
-        DCRF_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        DCRF_CUDA(copy_d2h(&h_bad, bad.p, sizeof(int), h->stream));
         DCRF_CUDA(cudaStreamSynchronize(h->stream));
         DCRF_REQUIRE(h_bad == 0, DCRF_EINVAL, "label out of range in unary_from_labels");
         h->unary_set = true;
@@ -799,6 +807,7 @@ int dcrf_add_pairwise_gaussian(dcrf_t *h, float sx, float sy, int compat_kind, c
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
         DCRF_REQUIRE(h->has_geom, DCRF_ESTATE, "addPairwiseGaussian needs a 2-D model");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         FeatureSpec fs;
         memset(&fs, 0, sizeof(fs));
         fs.mode = 0;
@@ -816,6 +825,7 @@ int dcrf_add_pairwise_bilateral(dcrf_t *h, float sx, float sy, float sr, float s
         DCRF_REQUIRE(h && rgb, DCRF_EINVAL, "NULL argument");
         DCRF_REQUIRE(h->has_geom, DCRF_ESTATE, "addPairwiseBilateral needs a 2-D model");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         DevBuf<uint8_t> stage;
         FeatureSpec fs;
         memset(&fs, 0, sizeof(fs));
@@ -835,6 +845,7 @@ int dcrf_add_pairwise_energy(dcrf_t *h, const float *features, int d, int on_dev
         DCRF_REQUIRE(h->geom.B == 1, DCRF_ESTATE, "addPairwiseEnergy is single-image only");
         DCRF_REQUIRE(d >= 1 && d <= kMaxD, DCRF_EINVAL, "feature dimension d must be in [1, 7]");
         DeviceGuard guard(h->device);
+        ProfGuard pguard(h);
         DevBuf<float> stage;
         FeatureSpec fs;
         memset(&fs, 0, sizeof(fs));
@@ -946,7 +957,7 @@ int dcrf_get_q_hwc(dcrf_t *h, float min_prob, int take_log, float *out, int on_d
             DevBuf<float> stage;
             stage.alloc(n, h->stream);
             launch_q_to_hwc(h->Q.p, stage.p, h->geom.Ntot, h->L, h->Lp, min_prob, renorm, take_log, h->stream);
-            DCRF_CUDA(cudaMemcpyAsync(out, stage.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+            DCRF_CUDA(copy_d2h(out, stage.p, sizeof(float) * n, h->stream));
             host_sync(h);
         }
     });
@@ -987,7 +998,7 @@ int dcrf_kl_divergence(dcrf_t *h, double *kl_out) {
         DevBuf<double> d_out;
         d_out.alloc(1, s);
         launch_kl(h->Q.p, h->unary.p, ptrs, (int)h->pw.size(), Ntot, h->L, h->Lp, d_out.p, s);
-        DCRF_CUDA(cudaMemcpyAsync(kl_out, d_out.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(copy_d2h(kl_out, d_out.p, sizeof(double), s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     });
 }
@@ -1055,24 +1066,21 @@ int dcrf_lattice_export(dcrf_t *h, int kernel, int image, int16_t *keys, int32_t
         std::vector<int2> nb;
         if (keys) {
             k8.resize((size_t)Mb * 8);
-            DCRF_CUDA(cudaMemcpyAsync(k8.data(), p.lat.vkeys.p + v0 * 8, sizeof(int16_t) * Mb * 8,
-                                      cudaMemcpyDeviceToHost, s));
+            DCRF_CUDA(copy_d2h(k8.data(), p.lat.vkeys.p + v0 * 8, sizeof(int16_t) * Mb * 8, s));
         }
         if (offsets)
-            DCRF_CUDA(cudaMemcpyAsync(offsets, p.lat.offset.p + p0 * d1, sizeof(int32_t) * Nb * d1,
-                                      cudaMemcpyDeviceToHost, s));
+            DCRF_CUDA(copy_d2h(offsets, p.lat.offset.p + p0 * d1, sizeof(int32_t) * Nb * d1, s));
         if (bary)
-            DCRF_CUDA(cudaMemcpyAsync(bary, p.lat.bary.p + p0 * d1, sizeof(float) * Nb * d1,
-                                      cudaMemcpyDeviceToHost, s));
+            DCRF_CUDA(copy_d2h(bary, p.lat.bary.p + p0 * d1, sizeof(float) * Nb * d1, s));
         if (neighbours) {
             nb.resize((size_t)Mb * d1);
             for (int j = 0; j < d1; j++)
-                DCRF_CUDA(cudaMemcpyAsync(nb.data() + (size_t)j * Mb, p.lat.neigh.p + (int64_t)j * p.lat.M + v0,
-                                          sizeof(int2) * Mb, cudaMemcpyDeviceToHost, s));
+                DCRF_CUDA(copy_d2h(nb.data() + (size_t)j * Mb, p.lat.neigh.p + (int64_t)j * p.lat.M + v0,
+                                          sizeof(int2) * Mb, s));
         }
         if (norm) {
             DCRF_REQUIRE(p.norm.p != nullptr, DCRF_ESTATE, "kernel has no norm (NO_NORMALIZATION)");
-            DCRF_CUDA(cudaMemcpyAsync(norm, p.norm.p + p0, sizeof(float) * Nb, cudaMemcpyDeviceToHost, s));
+            DCRF_CUDA(copy_d2h(norm, p.norm.p + p0, sizeof(float) * Nb, s));
         }
         DCRF_CUDA(cudaStreamSynchronize(s));
         if (keys)
@@ -1103,9 +1111,9 @@ int dcrf_expf_ref(const float *x, float *y, int64_t n, int device) {
         DevBuf<float> dx, dy;
         dx.alloc((size_t)n, s);
         dy.alloc((size_t)n, s);
-        DCRF_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(copy_h2d(dx.p, x, sizeof(float) * n, s));
         launch_expf_ref(dx.p, dy.p, n, s);
-        DCRF_CUDA(cudaMemcpyAsync(y, dy.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(copy_d2h(y, dy.p, sizeof(float) * n, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     });
 }
@@ -1127,12 +1135,12 @@ int dcrf_lattice_filter(dcrf_t *h, int kernel, const float *in, float *out, int 
         a.alloc((size_t)p.lat.M * vp, s);
         b.alloc((size_t)p.lat.M * vp, s);
         sl.alloc((size_t)N * vp, s);
-        DCRF_CUDA(cudaMemcpyAsync(ln.p, in, sizeof(float) * N * vs, cudaMemcpyHostToDevice, s));
+        DCRF_CUDA(copy_h2d(ln.p, in, sizeof(float) * N * vs, s));
         launch_ln_to_pm(ln.p, pm.p, h->geom, vs, vp, s);
         const float *blurred = filter_to_lattice(h, p, pm.p, vp, false, seq, a.p, b.p);
         launch_slice_plain(p.lat, blurred, sl.p, N, vp, seq, s);
         launch_pm_to_ln(sl.p, ln.p, h->geom, vs, vp, s);
-        DCRF_CUDA(cudaMemcpyAsync(out, ln.p, sizeof(float) * N * vs, cudaMemcpyDeviceToHost, s));
+        DCRF_CUDA(copy_d2h(out, ln.p, sizeof(float) * N * vs, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     });
 }

@@ -42,6 +42,18 @@ struct Error {
         DCRF_CUDA(cudaGetLastError());                 \
     } while (0)
 
+// every copy between caller / host memory and the device goes through these two (byte counters behind
+// dcrf_copy_count: tests assert that device-tensor calls move no payload over PCIe)
+extern std::atomic<int64_t> g_h2d_bytes, g_d2h_bytes;
+inline cudaError_t copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    g_h2d_bytes.fetch_add((int64_t)bytes);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+inline cudaError_t copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    g_d2h_bytes.fetch_add((int64_t)bytes);
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+}
+
 // One memory pool PER STREAM (created on first use, destroyed with dcrf_stream_destroy or at exit).
 // Every block is then allocated, freed and recycled in the order of ONE stream: no cross-stream
 // reuse, hence no hidden inter-stream dependencies and no pool growth after the first batches.

@@ -30,15 +30,17 @@ constexpr int kWarps = kThreads / 32;
 // lane -> (row within warp, float4 column); rows_per_warp = 32 / g
 template <int G>
 struct RowMap {
-    int g, rpw;
-    __device__ __forceinline__ explicit RowMap(int g_rt) {
+    int g, rpw, vb;
+    // vblock: the block index this CTA plays (persistent kernels loop over virtual blocks)
+    __device__ __forceinline__ explicit RowMap(int g_rt, int vblock = blockIdx.x) {
         g = G ? G : g_rt;
         rpw = 32 / g;
+        vb = vblock;
     }
     __device__ __forceinline__ int sub() const { return (threadIdx.x & 31) / g; }
     __device__ __forceinline__ int col() const { return (threadIdx.x & 31) % g; }
     __device__ __forceinline__ int64_t row() const {
-        return ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * rpw + sub();
+        return ((int64_t)vb * kWarps + (threadIdx.x >> 5)) * rpw + sub();
     }
     __device__ __forceinline__ bool lane_active() const { return sub() < rpw; }
 };
@@ -211,11 +213,10 @@ constexpr int kSplatLongRow = 256;
 constexpr int kSplatRefMinBlocks = DCRF_TUNE_SPLAT_REF_MINB;
 
 template <int G, int SB, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
-                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-                                                              const float4 *__restrict__ Q4,
-                                                              float4 *__restrict__ val4, int M, int g_rt,
-                                                              int *__restrict__ row_counter, int long_cap) {
+__device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_start,
+                                                const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                const float4 *__restrict__ Q4, float4 *__restrict__ val4, int M,
+                                                int g_rt, int *__restrict__ row_counter, int long_cap) {
     typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     const int g = G ? G : g_rt;
@@ -304,18 +305,26 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
     }
 }
 
+template <int G, int SB, bool REF>
+__global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M, int g_rt,
+                                                              int *__restrict__ row_counter, int long_cap) {
+    splat_fast_body<G, SB, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, row_counter, long_cap);
+}
+
 // Same schedule with COOPERATIVE entry loads: every warp-level load request costs the LSU a fixed
 // >= 6 cycles however few bytes it moves (tools/micro/bulk_gather.cu), and above each lane loads all
 // SB entries of its group's batch itself -- SB broadcast requests per SB gathers.  Here lane c of a
 // group loads entry c of the batch (one request per G entries) and the (pixel, weight) pairs are
 // broadcast inside the group with shuffles.  A trip handles NB * G entries.  Summation order and
 // arithmetic are unchanged, so the result is bit-identical to splat_fast_kernel.
-template <int G, int NB, int MINB, bool REF>
-__global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
-                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-                                                              const float4 *__restrict__ Q4,
-                                                              float4 *__restrict__ val4, int M,
-                                                              int *__restrict__ row_counter, int long_cap) {
+template <int G, int NB, bool REF>
+__device__ __forceinline__ void splat_coop_body(const int32_t *__restrict__ csr_start,
+                                                const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                const float4 *__restrict__ Q4, float4 *__restrict__ val4, int M,
+                                                int *__restrict__ row_counter, int long_cap) {
     typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int SB = G * NB;
@@ -408,6 +417,15 @@ __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_
     }
 }
 
+template <int G, int NB, int MINB, bool REF>
+__global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M,
+                                                              int *__restrict__ row_counter, int long_cap) {
+    splat_coop_body<G, NB, REF>(csr_start, csr_ent, Q4, val4, M, row_counter, long_cap);
+}
+
 // rows with more than long_cap entries (found at build time, any order: rows are independent)
 __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t *__restrict__ csr_start, int64_t M,
                                                                   int32_t *__restrict__ long_rows,
@@ -421,11 +439,10 @@ __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t 
 // lane group k sums entries k, k + n_groups, ... in order, then the groups are combined by a fixed
 // binary tree in shared memory => deterministic (but not the sequential order of the specification).
 template <int G, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
+__device__ __forceinline__ void splat_long_tail_body(
     const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
     const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
-    const int *__restrict__ n_long, int g_rt, int long_cap) {
-    extern __shared__ float4 part[];  // [n_groups][g]
+    const int *__restrict__ n_long, int g_rt, int long_cap, float4 *part /* shared [kThreads] */) {
     const int g = G ? G : g_rt;
     const int n_groups = kThreads / g;
     const int k = threadIdx.x / g, c = threadIdx.x - k * g;
@@ -461,6 +478,15 @@ __global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
         }
         __syncthreads();
     }
+}
+
+template <int G, bool REF>
+__global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
+    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
+    const int *__restrict__ n_long, int g_rt, int long_cap) {
+    extern __shared__ float4 part[];  // [n_groups][g]
+    splat_long_tail_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, part);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "common.cuh"
 
@@ -385,11 +386,14 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     rec_rank.alloc(Ntot, s);
     out.bary.alloc(E, s);
     const int nbp = ceil_div(Ntot, kThreads);
+    std::unique_ptr<ProfScope> prof(new ProfScope(DCRF_K_BUILD_POINT, D, s));
     lattice_point_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, f.mode, f.s[0], f.s[1], f.s[2], f.s[3],
                                                     f.s[4], f.rgb, f.features, scale, rec_rem.p,
                                                     rec_rank.p, out.bary.p);
     DCRF_LAUNCHED();
 
+    prof.reset();
+    prof.reset(new ProfScope(DCRF_K_BUILD_HASH, D, s));
     // per-image table regions: capacity = pow2 >= 1.25 * N_b * (d+1) entries, i.e. a load factor of at
     // most 0.8 in the worst case of all-distinct keys (natural images: M ~ 0.1 E, load < 0.1)
     std::vector<int64_t> tab_start(B + 1, 0);
@@ -405,9 +409,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     DevBuf<int> d_tab_mask;
     d_tab_start.alloc(B + 1, s);
     d_tab_mask.alloc(B, s);
-    DCRF_CUDA(cudaMemcpyAsync(d_tab_start.p, tab_start.data(), sizeof(int64_t) * (B + 1),
-                              cudaMemcpyHostToDevice, s));
-    DCRF_CUDA(cudaMemcpyAsync(d_tab_mask.p, tab_mask.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(copy_h2d(d_tab_start.p, tab_start.data(), sizeof(int64_t) * (B + 1), s));
+    DCRF_CUDA(copy_h2d(d_tab_mask.p, tab_mask.data(), sizeof(int) * B, s));
     DevBuf<int32_t> table;
     table.alloc(tab_start[B], s);
     DCRF_CUDA(cudaMemsetAsync(table.p, 0xFF, sizeof(int32_t) * tab_start[B], s));
@@ -418,6 +421,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
                                                   rec_rank.p, table.p, slot_of.p);
     DCRF_LAUNCHED();
 
+    prof.reset();
+    prof.reset(new ProfScope(DCRF_K_BUILD_NUMBER, D, s));
     DevBuf<int32_t> scanned;
     scanned.alloc(E + 1, s);
     const int nbe = ceil_div(E, kThreads);
@@ -431,8 +436,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     vert_start_kernel<<<ceil_div(B + 1, 128), 128, 0, s>>>(g.d_pix_start, B, d1, scanned.p, d_vert_start.p);
     DCRF_LAUNCHED();
     std::vector<int32_t> h_vs(B + 1);
-    DCRF_CUDA(cudaMemcpyAsync(h_vs.data(), d_vert_start.p, sizeof(int32_t) * (B + 1),
-                              cudaMemcpyDeviceToHost, s));
+    DCRF_CUDA(copy_d2h(h_vs.data(), d_vert_start.p, sizeof(int32_t) * (B + 1), s));
     DCRF_CUDA(cudaStreamSynchronize(s));
     out.vert_start.assign(h_vs.begin(), h_vs.end());
     const int64_t M = h_vs[B];
@@ -446,6 +450,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
                                              rec_rem.p, rec_rank.p, out.offset.p, vkeys4, ka.p, va.p);
     DCRF_LAUNCHED();
+    prof.reset();
+    prof.reset(new ProfScope(DCRF_K_BUILD_NEIGH, D, s));
     // Neighbour look-ups go through a second, COMPACT table of vertex ids (capacity = pow2 >= 2 M_b per
     // image, ~1 MB per VOC image: the batch's tables stay L2 resident), instead of the insertion table
     // that is sized for the worst case M = E (16 MB per image, every probe a DRAM access).
@@ -464,8 +470,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     d_tab2_start.alloc(B + 1, s);
     d_tab2_mask.alloc(B, s);
     table2.alloc(tab2_start[B], s);
-    DCRF_CUDA(cudaMemcpyAsync(d_tab2_start.p, tab2_start.data(), sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, s));
-    DCRF_CUDA(cudaMemcpyAsync(d_tab2_mask.p, tab2_mask.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(copy_h2d(d_tab2_start.p, tab2_start.data(), sizeof(int64_t) * (B + 1), s));
+    DCRF_CUDA(copy_h2d(d_tab2_mask.p, tab2_mask.data(), sizeof(int) * B, s));
     DCRF_CUDA(cudaMemsetAsync(table2.p, 0xFF, sizeof(int32_t) * tab2_start[B], s));
     compact_insert_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
                                                                     d_tab2_mask.p, vkeys4, table2.p);
@@ -479,6 +485,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     DCRF_CUDA(cudaStreamSynchronize(s));  // tab2_* host vectors are read by the async copies above
 
     // transposed incidence rows: stable sort of entries by vertex id
+    prof.reset();
+    prof.reset(new ProfScope(DCRF_K_BUILD_SORT, D, s));
     kb.alloc(E, s); vb.alloc(E, s);
     // per-image segments: keys local to an image need fewer radix passes than batch-global ids
     int64_t max_mb = 1;
@@ -489,6 +497,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     while (((int64_t)1 << bits) < max_mb) bits++;
     const int in_b = segmented_radix_sort_pairs(ka.p, va.p, kb.p, vb.p, ent_start, d_vert_start.p, bits, s);
     const uint32_t *sk = in_b ? kb.p : ka.p, *sv = in_b ? vb.p : va.p;
+    prof.reset();
+    prof.reset(new ProfScope(DCRF_K_BUILD_CSR, D, s));
     out.csr_start.alloc(M + 1, s);
     out.csr_pix.alloc(E, s);
     out.csr_w.alloc(E, s);
@@ -575,6 +585,7 @@ void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, 
                               float *norm_out, cudaStream_t s) {
     const int d1 = one.d + 1;
     const int64_t M = one.M, E = one.E;
+    ProfScope prof(DCRF_K_BUILD_REPL, one.d, s);
     DCRF_REQUIRE(E * B < (int64_t)2147483000, DCRF_EINVAL, "batch too large: N*(d+1) must stay below 2^31");
     out.d = one.d;
     out.M = M * B;

@@ -327,8 +327,8 @@ int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *key
     DevBuf<int32_t> d_seg, d_tile, hist;
     d_seg.alloc(S + 1, s);
     d_tile.alloc(S + 1, s);
-    DCRF_CUDA(cudaMemcpyAsync(d_seg.p, h_seg.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice, s));
-    DCRF_CUDA(cudaMemcpyAsync(d_tile.p, h_tile.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice, s));
+    DCRF_CUDA(copy_h2d(d_seg.p, h_seg.data(), sizeof(int32_t) * (S + 1), s));
+    DCRF_CUDA(copy_h2d(d_tile.p, h_tile.data(), sizeof(int32_t) * (S + 1), s));
     DCRF_CUDA(cudaStreamSynchronize(s));  // host vectors go out of scope
     hist.alloc((size_t)radix * total_tiles + 1, s);
     SegInfo si{d_seg.p, d_key_base, d_tile.p, S};

@@ -585,3 +585,10 @@ def trim_memory():
 def launch_count():
     """Kernels launched by libdcrf_b200.so in this process (bench.py reports it as gpu_launches)."""
     return int(_lib.load().dcrf_launch_count())
+
+
+def copy_count():
+    """(host->device bytes, device->host bytes) copied by libdcrf_b200.so in this process so far."""
+    a, b = C.c_int64(0), C.c_int64(0)
+    _lib.load().dcrf_copy_count(C.byref(a), C.byref(b))
+    return a.value, b.value

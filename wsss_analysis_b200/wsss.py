@@ -16,7 +16,7 @@ unary construction the reference also does in NumPy; the CRF itself has no CPU p
 """
 import numpy as np
 
-from .densecrf import DenseCRFBatch
+from .densecrf import DenseCRFBatch, _is_torch
 from .utils import unary_from_labels, unary_from_softmax  # noqa: F401  (host forms, kept for callers)
 
 __all__ = ["dcrf_process", "crf_inference", "crf_inference_batch", "sec_crf_layer", "crf_inference_label",
@@ -24,6 +24,13 @@ __all__ = ["dcrf_process", "crf_inference", "crf_inference_batch", "sec_crf_laye
 
 # [EXT] defaults of jiwoon-ahn/irn `crf_inference_label` (last row)
 IRN_CRF_CONFIG = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 50, "bi_srgb": 5, "bi_compat": 10, "iterations": 10}
+
+
+def _on_gpu(x):
+    """torch CUDA tensor?  Such inputs stay on the GPU: unaries, images, marginals and label maps are
+    handed to / returned by the library as device pointers and the result is a
+    CUDA tensor; only a few hundred bytes of batch geometry cross PCIe."""
+    return _is_torch(x) and x.is_cuda
 
 
 def _active_classes(probs_img):
@@ -67,6 +74,8 @@ def dcrf_process(probs, images, config, device=None):
 
     Images are grouped by their number of active classes and each group runs as one batch."""
     gauss_sxy, gauss_compat, bilat_sxy, bilat_srgb, bilat_compat, n_infer = config
+    if _on_gpu(probs):
+        return _dcrf_process_device(probs, images, config)
     probs = np.asarray(probs)
     num_input_images, num_classes = probs.shape[0], probs.shape[1]
     size = images.shape[1:3]
@@ -95,6 +104,39 @@ def dcrf_process(probs, images, config, device=None):
     return out
 
 
+def _dcrf_process_device(probs, images, config):
+    """dcrf_process for CUDA tensors: probs (B, C, H, W) float64 / float32, images (B, H, W, 3) any
+    dtype; returns a (B, H, W) int64 CUDA tensor.  Only the (B, C) table of active classes is read on
+    the host (it decides how the images are grouped into batches)."""
+    import torch
+
+    gauss_sxy, gauss_compat, bilat_sxy, bilat_srgb, bilat_compat, n_infer = config
+    B, C_, H, W = (int(v) for v in probs.shape)
+    dev = probs.device
+    if probs.dtype not in (torch.float32, torch.float64):
+        probs = probs.to(torch.float64)
+    img8 = images.to(device=dev, dtype=torch.uint8).contiguous()          # np.uint8(images[i]) of utilities.py:439
+    act_mask = (probs.sum(dim=(2, 3)) > 0).cpu().numpy()                   # utilities.py:425
+    active = [np.flatnonzero(act_mask[i]) for i in range(B)]
+    out = torch.zeros((B, H, W), dtype=torch.int64, device=dev)
+    groups = []
+    for n_act, members in _group_by([len(a) for a in active]).items():
+        groups += [(n_act, c) for c in _chunks(members, [H * W] * B)]
+    for n_act, idx in groups:
+        if n_act == 0:
+            continue
+        act_t = [torch.as_tensor(active[i], device=dev) for i in idx]
+        d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=dev.index)
+        d.setUnaryFromSoftmax(torch.cat([probs[i].index_select(0, a).reshape(-1) for i, a in zip(idx, act_t)]))
+        d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
+        d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=img8[idx].contiguous(), compat=bilat_compat)
+        labels = d.map_device(n_infer).view(len(idx), H, W).long()
+        d.close()
+        for j, (i, a) in enumerate(zip(idx, act_t)):
+            out[i] = a[labels[j]]
+    return out
+
+
 def _unary_from_featmap(feat, use_log=True):
     """[EXT] unary of SEC's crf_inference(use_log=True): softmax over the class axis then -log,
     returned as C-contiguous (C, H*W) float32.  (Host form kept for callers / tests; the batched path
@@ -117,6 +159,24 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
     """Batched `crf_inference`: imgs list of (H_b, W_b, 3) uint8, featmaps list of (H_b, W_b, C).
     Returns a list of (H_b, W_b, C) float32 marginals (written in that layout by the GPU).
     `min_prob` / `log`: the clamp + renormalise + log epilogue of the SEC / DSRG `crf` closure."""
+    if _on_gpu(featmaps):
+        # (B, H, W, C) float32 feature maps + (B, H, W, 3) images as CUDA tensors -> (B, H, W, C) CUDA tensor
+        import torch
+
+        B, H, W, C_ = (int(v) for v in featmaps.shape)
+        dev = featmaps.device
+        img8 = imgs.to(device=dev, dtype=torch.uint8).contiguous()
+        res = torch.empty((B, H, W, C_), dtype=torch.float32, device=dev)
+        for idx in _chunks(range(B), [H * W] * B):
+            d = DenseCRFBatch([(W, H)] * len(idx), num_classes, device=dev.index)
+            d.setUnaryFromLogits(featmaps[idx[0]:idx[-1] + 1].to(torch.float32).contiguous(), use_log)
+            d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
+            d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
+                                   rgbim=img8[idx[0]:idx[-1] + 1], compat=crf_config["bi_compat"])
+            d.run(crf_config["iterations"])
+            d.marginals_hwc_device(out=res[idx[0]:idx[-1] + 1].view(-1), min_prob=min_prob, log=log)
+            d.close()
+        return res
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     out = [None] * len(imgs)
     for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
@@ -145,7 +205,11 @@ def crf_inference(img, crf_config, num_classes, featmap, use_log=True, device=No
 def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, device=None):
     """The `crf` closure run through tf.py_func in SEC.py:270-280 / DSRG.py:323-332, whole batch in
     one handle: featemap (B, h, w, C) float32, image (B, h, w, 3) float -> uint8;
-    returns log of the clamped (>= min_prob), renormalised marginals, (B, h, w, C) float32."""
+    returns log of the clamped (>= min_prob), renormalised marginals, (B, h, w, C) float32.
+    CUDA tensors in -> CUDA tensor out (the training hook of SURVEY.md 8f rank 2: nothing but batch
+    geometry crosses PCIe)."""
+    if _on_gpu(featemap):
+        return crf_inference_batch(image, crf_config, num_classes, featemap, use_log=True, min_prob=min_prob, log=True)
     featemap = np.asarray(featemap)
     batch_size = featemap.shape[0]
     image = np.asarray(image).astype(np.uint8)
@@ -169,6 +233,26 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
     the unary -- the VOC branch of cam_to_ir_label.py runs the CRF twice per image (fg threshold
     :47, bg threshold :52).  With extra sets the return value is a list of result lists."""
     cfg = dict(IRN_CRF_CONFIG if crf_config is None else crf_config)
+    if _on_gpu(imgs):
+        # (B, H, W, 3) images and (B, H, W) label maps as CUDA tensors -> (B, H, W) int64 CUDA tensor(s)
+        import torch
+
+        B, H, W = (int(v) for v in imgs.shape[:3])
+        dev = imgs.device
+        img8 = imgs.to(torch.uint8).contiguous()
+        sets = [labels] + list(extra_labels)
+        res = [torch.empty((B, H, W), dtype=torch.int64, device=dev) for _ in sets]
+        for idx in _chunks(range(B), [H * W] * B):
+            lo, hi = idx[0], idx[-1] + 1
+            d = DenseCRFBatch([(W, H)] * len(idx), n_labels, device=dev.index)
+            d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
+            d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"], rgbim=img8[lo:hi], compat=cfg["bi_compat"])
+            for k, ls in enumerate(sets):
+                d.setUnaryFromLabels(ls[lo:hi].to(device=dev, dtype=torch.int32).contiguous(), gt_prob=gt_prob,
+                                     zero_unsure=False)
+                res[k][lo:hi] = d.map_device(t).view(len(idx), H, W)
+            d.close()
+        return res[0] if not extra_labels else res
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     label_sets = [labels] + list(extra_labels)
     outs = [[None] * len(imgs) for _ in label_sets]
