@@ -124,7 +124,12 @@ enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2, DCRF
  * Host buffers should be page-locked, otherwise the copies are not asynchronous.  In this mode
  * dcrf_set_unary runs its upload and layout change on a separate per-thread stream, so the lattice
  * builds enqueued next overlap the upload; the handle's stream waits for it before the unary is read. */
-enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2 };
+/* DCRF_OPT_PERSISTENT: dcrf_inference / dcrf_map / dcrf_run of a small problem (<= 400 000 pixels in the
+ * handle: one VOC image, a training batch of 41x41 maps; DCRF_PERSISTENT_MAX_PIXELS overrides) run as ONE
+ * cooperative launch with grid barriers between the phases instead of ~16 launches per iteration.
+ * -1 (default) = by problem size, 0 = never, 1 = whenever the model allows (Potts terms, > 2 labels).
+ * Same arithmetic, bit-identical marginals. */
+enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2, DCRF_OPT_PERSISTENT = 4 };
 int dcrf_set_option(dcrf_t *h, int option, int value);
 int dcrf_get_arithmetic(dcrf_t *h, int *mode_out);
 /* block the calling thread until everything enqueued on the handle's stream has finished */

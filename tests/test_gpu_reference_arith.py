@@ -203,3 +203,58 @@ def test_arithmetic_option_can_change_after_the_kernels_were_added():
     assert np.array_equal(_bits(Qr), _bits(Qo))
     assert np.array_equal(_bits(g.inference(4)), _bits(Qf))
     assert 0 < np.abs(Qf - Qo).max() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["fma", "reference", "strict"])
+@pytest.mark.parametrize("shape", [(96, 72, 21, "natural"), (120, 90, 6, "natural"), (64, 64, 29, "histo"),
+                                   (160, 120, 21, "flat"), (41, 41, 13, "iid")])
+def test_persistent_kernel_is_bit_identical_to_the_launch_per_phase_path(mode, shape):
+    """Small problems run inference(n) as one cooperative launch (mean_field_persistent_kernel): same
+    device bodies, same summation order => the same bits, for every lane-group width and on flat
+    images (long-row tails)."""
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+
+    W, H, L, kind = shape
+    img = np.full((H, W, 3), 200, np.uint8) if kind == "flat" else getattr(S, kind + "_image")(H, W, 3)
+    U = S.random_unary(L, W * H, 3)
+    Q = []
+    for persistent in (False, True):
+        g = G.DenseCRF2D(W, H, L)
+        g.set_arithmetic(mode)
+        g.set_persistent(persistent)
+        g.setUnaryEnergy(U)
+        g.addPairwiseGaussian(sxy=3, compat=3)
+        g.addPairwiseBilateral(sxy=50, srgb=13, rgbim=img, compat=10)
+        n0 = G.launch_count()
+        Q.append(g.inference(7))
+        launches = G.launch_count() - n0
+        assert (launches <= 3) == persistent, launches    # persistent: the kernel + the layout change of the output
+        assert np.array_equal(g.map(7), Q[-1].argmax(0).astype(np.int32))
+    assert np.array_equal(_bits(Q[0]), _bits(Q[1]))
+
+
+def test_persistent_batch_of_sec_maps_matches_oracle():
+    """BASELINE config 2: a batch of 41x41 maps (SEC.py:19) goes through the persistent kernel by
+    default; every map against the oracle."""
+    from oracle import oracle as O
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+
+    B, W, H, L = 32, 41, 41, 21
+    imgs = [S.natural_image(H, W, 50 + b) for b in range(B)]
+    Us = [S.random_unary(L, W * H, 50 + b) for b in range(B)]
+    d = G.DenseCRFBatch([(W, H)] * B, L)
+    d.set_arithmetic("strict")
+    d.setUnaryEnergy(Us)
+    d.addPairwiseGaussian(sxy=3 / 12, compat=3)
+    d.addPairwiseBilateral(sxy=80 / 12, srgb=13, rgbim=imgs, compat=10)
+    n0 = G.launch_count()
+    Q = d.inference(5)
+    assert G.launch_count() - n0 <= 3
+    for b in range(0, B, 5):
+        o = O.DenseCRF2D(W, H, L)
+        o.setUnaryEnergy(Us[b])
+        o.addPairwiseGaussian(sxy=3 / 12, compat=3)
+        o.addPairwiseBilateral(sxy=80 / 12, srgb=13, rgbim=imgs[b], compat=10)
+        assert np.array_equal(_bits(o.inference(5)), _bits(Q[b]))

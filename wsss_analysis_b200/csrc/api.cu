@@ -197,8 +197,10 @@ struct dcrf_handle {
     BatchGeom geom;
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
+    DevBuf<int> counters;  // row dispensers of the persistent mean-field kernel
     bool unary_set = false, q_valid = false;
     int arith = kArithFma;    // resolved arithmetic: kArithFma / kArithRef / kArithStrict
+    int persistent = -1;      // DCRF_OPT_PERSISTENT: -1 = by problem size, 0 = never, 1 = whenever the model allows
     bool arith_auto = true;   // DCRF_ARITH_AUTO: `arith` follows the conditioning of the pairwise terms
     bool async_host = false;  // DCRF_OPT_ASYNC_HOST
     std::vector<std::unique_ptr<Pairwise>> pw;
@@ -551,8 +553,50 @@ void emit_labels(dcrf_handle *h, T *labels_out, int on_device) {
     }
 }
 
+// Small problems (one VOC image, a batch of SEC's 41x41 maps) run the whole of inference(n) as one
+// cooperative launch (filter.cu, mean_field_persistent_kernel); DCRF_PERSISTENT_MAX_PIXELS moves the
+// threshold (0 disables the path).
+bool try_persistent(dcrf_handle *h, int n_iter) {
+    static const int64_t max_pix = [] {
+        const char *e = getenv("DCRF_PERSISTENT_MAX_PIXELS");
+        return e ? (int64_t)atoll(e) : (int64_t)400000;
+    }();
+    const int n = (int)h->pw.size();
+    if (h->persistent == 0 || (h->persistent < 0 && h->geom.Ntot > max_pix)) return false;
+    if (h->prof.on || h->L <= 2 || n == 0 || n_iter < 1 || h->Lp > 32) return false;
+    int64_t max_rows = h->geom.Ntot;
+    for (auto &p : h->pw) {
+        if (p->compat_kind != DCRF_COMPAT_POTTS || p->lat.M == 0) return false;
+        max_rows = std::max<int64_t>(max_rows, p->lat.M);
+    }
+    if (max_rows * (int64_t)(h->Lp / 4) >= ((int64_t)1 << 31)) return false;
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.fast = h->arith == kArithFma ? kSliceFma : kSliceRef;
+    a.max_rows = max_rows;
+    const Lattice *lats[kMaxPairwise];
+    float *va[kMaxPairwise], *vb[kMaxPairwise];
+    for (int k = 0; k < n; k++) {
+        Pairwise &p = *h->pw[k];
+        if (p.lat.table_mode != wanted_tables(h)) pack_tables(h, p.lat, p.ntype, p.norm.p, h->stream);
+        a.term[a.n_terms++] = make_term(p, nullptr);
+        lats[k] = &p.lat;
+        va[k] = p.valA.p;
+        vb[k] = p.valB.p;
+    }
+    h->counters.alloc((size_t)n_iter * n, h->stream);
+    return launch_mean_field_persistent(lats, va, vb, a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, n_iter,
+                                        h->counters.p, h->stream);
+}
+
 void run_inference(dcrf_handle *h, int n_iter) {
     DCRF_REQUIRE(n_iter >= 0, DCRF_EINVAL, "n_iter must be >= 0");
+    DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
+    join_upload(h);
+    if (try_persistent(h, n_iter)) {
+        h->q_valid = true;
+        return;
+    }
     start_inference(h);
     for (int it = 0; it < n_iter; it++) step_inference(h);
 }
@@ -606,6 +650,7 @@ void dcrf_destroy(dcrf_t *h) {
         h->pw.clear();
         h->unary.release();
         h->Q.release();
+        h->counters.release();
         h->d_w.release();
         h->d_h.release();
         h->d_pix_start.release();
@@ -668,8 +713,13 @@ int dcrf_stream_destroy(void *stream) {
 int dcrf_set_option(dcrf_t *h, int option, int value) {
     return guarded([&] {
         DCRF_REQUIRE(h, DCRF_EINVAL, "NULL handle");
-        DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC || option == DCRF_OPT_ASYNC_HOST, DCRF_EINVAL,
-                     "unknown option");
+        DCRF_REQUIRE(option == DCRF_OPT_EXACT_ARITHMETIC || option == DCRF_OPT_ASYNC_HOST ||
+                         option == DCRF_OPT_PERSISTENT, DCRF_EINVAL, "unknown option");
+        if (option == DCRF_OPT_PERSISTENT) {
+            DCRF_REQUIRE(value >= -1 && value <= 1, DCRF_EINVAL, "DCRF_OPT_PERSISTENT takes -1, 0 or 1");
+            h->persistent = value;
+            return;
+        }
         if (option == DCRF_OPT_EXACT_ARITHMETIC) {
             DCRF_REQUIRE(value >= 0 && value <= 3, DCRF_EINVAL, "arithmetic mode must be 0, 1, 2 or 3");
             if (value == DCRF_ARITH_AUTO) {  // re-derive from the terms added so far

@@ -237,6 +237,12 @@ void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int 
 // Q <- softmax_L( -U - sum_k compat_k( norm_k (.) slice_k ) )   (A.4 slice, A.5, A.6, A.7)
 void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int64_t Ntot, int L,
                           int Lp, cudaStream_t s);
+// `inference(n)` of a small problem as ONE cooperative launch (grid barriers between the phases); all
+// terms Potts, packed tables of the arithmetic in slice.fast.  counters: device int[n_iter * n_terms].
+// Returns false when the configuration is not covered (nothing launched).
+bool launch_mean_field_persistent(const Lattice *const *lats, float *const *valA, float *const *valB,
+                                  const SliceArgs &slice, const float *unary, float *Q, int64_t Ntot, int L, int Lp,
+                                  int n_iter, int *counters, cudaStream_t s);
 // plain slice of one lattice into a pixel-major buffer: out[p] = sum_r w v alpha (seq selects the
 // value_size<=2 association)
 void launch_slice_plain(const Lattice &lat, const float *val, float *out, int64_t Ntot, int Lp,

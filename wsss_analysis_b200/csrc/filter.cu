@@ -10,7 +10,10 @@
 // multiple of 4, pad lanes always 0.  A row is handled by G = Lp/4 adjacent lanes, one float4 each,
 // so every global access is a 128-bit access and a warp touches 32/G consecutive rows.
 // HBM-bound byte work: no tensor cores.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -510,21 +513,21 @@ constexpr int kBlurUnroll = DCRF_TUNE_BLUR_UNROLL;
 #endif
 constexpr int kBlurThreads = DCRF_TUNE_BLUR_THREADS;
 
-template <int G, bool SEQ>
-__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const int2 *__restrict__ neigh,
-                                                        const float *__restrict__ in,
-                                                        float *__restrict__ out, int64_t M, int g_rt) {
+// one tile of THREADS * BU float4 elements (tile index = blockIdx.x in the stand-alone kernel)
+template <int G, bool SEQ, int THREADS>
+__device__ __forceinline__ void blur_tile(const int2 *__restrict__ neigh, const float *__restrict__ in,
+                                          float *__restrict__ out, int64_t M, int g_rt, int64_t tile) {
     constexpr int BU = kBlurUnroll;
     const int g = G ? G : g_rt;
     const int64_t total = M * g;
-    const int64_t base = (int64_t)blockIdx.x * (kBlurThreads * BU) + threadIdx.x;
+    const int64_t base = tile * (THREADS * BU) + threadIdx.x;
     int64_t idx[BU];
     int c[BU];
     int2 nb[BU];
     float4 o[BU], a[BU], b[BU];
 #pragma unroll
     for (int u = 0; u < BU; u++) {
-        idx[u] = base + (int64_t)u * kBlurThreads;
+        idx[u] = base + (int64_t)u * THREADS;
         const bool ok = idx[u] < total;
         const int64_t v = ok ? idx[u] / g : 0;
         c[u] = (int)(idx[u] - v * g);
@@ -549,6 +552,13 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const int2 *__restri
             st4(out + idx[u] * 4, r);
         }
     }
+}
+
+template <int G, bool SEQ>
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const int2 *__restrict__ neigh,
+                                                        const float *__restrict__ in,
+                                                        float *__restrict__ out, int64_t M, int g_rt) {
+    blur_tile<G, SEQ, kBlurThreads>(neigh, in, out, M, g_rt, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -816,11 +826,10 @@ __global__ void __launch_bounds__(kThreads, G ? 2048 / kThreads : 1) slice_softm
 // Fast fused slice for any other combination of Potts terms (1..4 terms, any dimensions): same
 // arithmetic as above with run-time loops.
 template <int G>
-__global__ void __launch_bounds__(kThreads) slice_softmax_fast_generic_kernel(const SliceArgs a,
-                                                                              const float4 *__restrict__ unary4,
-                                                                              float4 *__restrict__ Q4, unsigned Ntot,
-                                                                              int L, int g_rt) {
-    const RowMap<G> rm(g_rt);
+__device__ __forceinline__ void slice_softmax_fast_generic_body(const SliceArgs &a, const float4 *__restrict__ unary4,
+                                                                float4 *__restrict__ Q4, unsigned Ntot, int L,
+                                                                int g_rt, int vblock) {
+    const RowMap<G> rm(g_rt, vblock);
     const unsigned g = rm.g, c = rm.col();
     const int64_t p64 = rm.row();
     const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
@@ -865,6 +874,14 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_fast_generic_kernel(co
         const float inv = 1.0f / sum;
         Q4[p * g + c] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) slice_softmax_fast_generic_kernel(const SliceArgs a,
+                                                                              const float4 *__restrict__ unary4,
+                                                                              float4 *__restrict__ Q4, unsigned Ntot,
+                                                                              int L, int g_rt) {
+    slice_softmax_fast_generic_body<G>(a, unary4, Q4, Ntot, L, g_rt, blockIdx.x);
 }
 
 // Q0 = softmax(-U) (startInference), fast-math variant of slice_softmax_kernel with no terms
@@ -1000,9 +1017,10 @@ __global__ void __launch_bounds__(kThreads, G ? DCRF_TUNE_REF_MINB : 1) slice_so
 
 // any other combination of Potts terms (0..4 terms, any dimensions; n_terms = 0 is startInference)
 template <int G>
-__global__ void __launch_bounds__(kThreads) slice_softmax_ref_generic_kernel(
-    const SliceArgs a, const float4 *__restrict__ unary4, float4 *__restrict__ Q4, unsigned Ntot, int L, int g_rt) {
-    const RowMap<G> rm(g_rt);
+__device__ __forceinline__ void slice_softmax_ref_generic_body(const SliceArgs &a, const float4 *__restrict__ unary4,
+                                                               float4 *__restrict__ Q4, unsigned Ntot, int L,
+                                                               int g_rt, int vblock) {
+    const RowMap<G> rm(g_rt, vblock);
     const unsigned g = rm.g, c = rm.col();
     const int64_t p64 = rm.row();
     const bool act = rm.lane_active() && p64 < (int64_t)Ntot;
@@ -1019,6 +1037,12 @@ __global__ void __launch_bounds__(kThreads) slice_softmax_ref_generic_kernel(
     const ExpfRef ex;
     const float4 q = softmax_ref_row<G>(t, L, (int)c, (int)g, gb, ex);
     if (act) Q4[p * g + c] = q;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) slice_softmax_ref_generic_kernel(
+    const SliceArgs a, const float4 *__restrict__ unary4, float4 *__restrict__ Q4, unsigned Ntot, int L, int g_rt) {
+    slice_softmax_ref_generic_body<G>(a, unary4, Q4, Ntot, L, g_rt, blockIdx.x);
 }
 
 // slice of one lattice without any epilogue (norm construction, test hook)
@@ -1336,6 +1360,103 @@ __global__ void kl_final_kernel(const double *__restrict__ partial, double *__re
         __syncthreads();
     }
     if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent mean field for SMALL problems (one VOC image, a batch of 41x41 SEC maps): the whole of
+// `inference(n)` -- Q0 = softmax(-U), then n x [splat, (long-row tails), d+1 blurs, fused slice] -- as
+// ONE cooperative launch with grid barriers between the phases.  With a kernel per phase such
+// problems are launch-latency bound (~16 launches of 5-20 us per iteration); here an iteration costs
+// its work plus ~9 grid barriers.  The phases run the same device bodies as the stand-alone kernels
+// (same arithmetic, same summation order), so the marginals are bit-identical to the launch-per-phase
+// path in every arithmetic mode.
+// ---------------------------------------------------------------------------------------------
+struct MfTerm {
+    const int32_t *csr_start;
+    const void *csr_ent;  // int2 (FMA tables) or int4 (reference tables)
+    const int2 *neigh;
+    const int32_t *long_rows;
+    const int *n_long;
+    float *valA, *valB;
+    int M, d, long_cap, long_hint;
+};
+struct MfArgs {
+    MfTerm term[kMaxPairwise];
+    SliceArgs slice;  // term[k].val is set inside the kernel (the blurred buffer of the iteration)
+    const float4 *unary4;
+    float4 *Q4;
+    unsigned Ntot;
+    int L, g, n_iter;
+    int *counters;  // [n_iter * n_terms] row dispensers of the splats, zeroed before the launch
+};
+
+template <int G, bool REF>
+__global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const MfArgs a) {
+    namespace cg = cooperative_groups;
+    typedef typename CsrEnt<REF>::type Ent;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float4 part[kThreads];
+    const int nblk = gridDim.x, g = a.g, nt = a.slice.n_terms;
+    const int n_slice_blocks = (int)(((int64_t)a.Ntot + kWarps * (32 / g) - 1) / (kWarps * (32 / g)));
+    SliceArgs sa = a.slice;
+    {   // Q0 = softmax(-U)
+        SliceArgs s0 = sa;
+        s0.n_terms = 0;
+        for (int vb = blockIdx.x; vb < n_slice_blocks; vb += nblk) {
+            if (REF) slice_softmax_ref_generic_body<G>(s0, a.unary4, a.Q4, a.Ntot, a.L, g, vb);
+            else slice_softmax_fast_generic_body<G>(s0, a.unary4, a.Q4, a.Ntot, a.L, g, vb);
+        }
+    }
+    grid.sync();
+    int dmax = 0;
+    for (int k = 0; k < nt; k++) dmax = max(dmax, a.term[k].d);
+    for (int it = 0; it < a.n_iter; it++) {
+        // splat of every term (dynamic row queues: no barrier between the terms)
+        bool any_long = false;
+        for (int k = 0; k < nt; k++) {
+            const MfTerm &t = a.term[k];
+            int *ctr = a.counters + it * nt + k;
+            float4 *v4 = reinterpret_cast<float4 *>(t.valA);
+            const Ent *ents = reinterpret_cast<const Ent *>(t.csr_ent);
+            if (G >= 4 && G <= 8) {
+                splat_coop_body<(G >= 4 && G <= 8) ? G : 4, 1, REF>(t.csr_start, ents, a.Q4, v4, t.M, ctr, t.long_cap);
+            } else if (t.long_hint) {
+                splat_fast_body<G, 8, REF>(t.csr_start, ents, a.Q4, v4, t.M, g, ctr, t.long_cap);
+            } else {
+                splat_fast_body<G, kSplatBatch, REF>(t.csr_start, ents, a.Q4, v4, t.M, g, ctr, t.long_cap);
+            }
+            any_long = any_long || *t.n_long > 0;  // written at build time: the same value in every CTA
+        }
+        grid.sync();
+        if (any_long) {
+            for (int k = 0; k < nt; k++) {
+                const MfTerm &t = a.term[k];
+                splat_long_tail_body<G, REF>(t.csr_start, reinterpret_cast<const Ent *>(t.csr_ent), a.Q4,
+                                             reinterpret_cast<float4 *>(t.valA), t.long_rows, t.n_long, g, t.long_cap,
+                                             part);
+            }
+            grid.sync();
+        }
+        // blurs: axis j of every term that has it, ping-pong A <-> B
+        for (int j = 0; j <= dmax; j++) {
+            for (int k = 0; k < nt; k++) {
+                const MfTerm &t = a.term[k];
+                if (j > t.d) continue;
+                const float *in = (j & 1) ? t.valB : t.valA;
+                float *out = (j & 1) ? t.valA : t.valB;
+                const int64_t tiles = ((int64_t)t.M * g + kThreads * kBlurUnroll - 1) / (kThreads * kBlurUnroll);
+                for (int64_t tile = blockIdx.x; tile < tiles; tile += nblk)
+                    blur_tile<G, false, kThreads>(t.neigh + (int64_t)j * t.M, in, out, t.M, g, tile);
+            }
+            grid.sync();
+        }
+        for (int k = 0; k < nt; k++) sa.term[k].val = ((a.term[k].d + 1) & 1) ? a.term[k].valB : a.term[k].valA;
+        for (int vb = blockIdx.x; vb < n_slice_blocks; vb += nblk) {
+            if (REF) slice_softmax_ref_generic_body<G>(sa, a.unary4, a.Q4, a.Ntot, a.L, g, vb);
+            else slice_softmax_fast_generic_body<G>(sa, a.unary4, a.Q4, a.Ntot, a.L, g, vb);
+        }
+        if (it + 1 < a.n_iter) grid.sync();
+    }
 }
 
 // dispatch on G = Lp/4 (1..8 specialised, anything else through the runtime-g instantiation)
@@ -1741,6 +1862,77 @@ void launch_unary_from_labels(const int32_t *labels, float *pm, int64_t Ntot, in
     unary_from_labels_kernel<<<ceil_div(Ntot * Lp, kThreads), kThreads, 0, s>>>(
         labels, pm, Ntot, L, Lp, n_energy, p_energy, unsure_energy, zero_unsure, bad);
     DCRF_LAUNCHED();
+}
+
+
+// persistent path: returns false when the configuration is not covered (caller falls back to the
+// launch-per-phase path)
+template <int G, bool REF>
+static bool launch_persistent_g(const MfArgs &a, cudaStream_t s) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        int n = 0;
+        DCRF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mean_field_persistent_kernel<G, REF>, kThreads, 0));
+        const char *e = getenv("DCRF_PERSISTENT_CTAS_PER_SM");
+        const int want = e ? atoi(e) : 3;
+        per_sm = std::max(1, std::min(n, want > 0 ? want : n));
+    }
+    void *params[] = {(void *)&a};
+    DCRF_CUDA(cudaLaunchCooperativeKernel((const void *)mean_field_persistent_kernel<G, REF>, dim3(kNumSMs * per_sm),
+                                          dim3(kThreads), params, 0, s));
+    DCRF_LAUNCHED();
+    return true;
+}
+
+bool launch_mean_field_persistent(const Lattice *const *lats, float *const *valA, float *const *valB,
+                                  const SliceArgs &slice, const float *unary, float *Q, int64_t Ntot, int L, int Lp,
+                                  int n_iter, int *counters, cudaStream_t s) {
+    const int g = Lp / 4;
+    if (g < 1 || g > 8 || slice.n_terms < 1) return false;
+    const bool ref = slice.fast == kSliceRef;
+    if (!ref && slice.fast != kSliceFma) return false;
+    MfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.slice = slice;
+    for (int k = 0; k < slice.n_terms; k++) {
+        const Lattice &lat = *lats[k];
+        if (lat.M <= 0 || lat.table_mode != (ref ? kTablesRef : kTablesFma)) return false;
+        MfTerm &t = a.term[k];
+        t.csr_start = lat.csr_start.p;
+        t.csr_ent = ref ? (const void *)lat.csr_ent4.p : (const void *)lat.csr_ent.p;
+        t.neigh = lat.neigh.p;
+        t.long_rows = lat.long_rows.p;
+        t.n_long = lat.n_long.p;
+        t.valA = valA[k];
+        t.valB = valB[k];
+        t.M = (int)lat.M;
+        t.d = lat.d;
+        t.long_cap = lat.long_row_cap;
+        t.long_hint = lat.E >= 16 * lat.M ? 1 : 0;
+    }
+    a.unary4 = reinterpret_cast<const float4 *>(unary);
+    a.Q4 = reinterpret_cast<float4 *>(Q);
+    a.Ntot = (unsigned)Ntot;
+    a.L = L;
+    a.g = g;
+    a.n_iter = n_iter;
+    a.counters = counters;
+    DCRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * std::max(1, n_iter * slice.n_terms), s));
+    switch (g) {
+#define DCRF_PERSIST_CASE(GG)                                        \
+    case GG:                                                         \
+        return ref ? launch_persistent_g<GG, true>(a, s) : launch_persistent_g<GG, false>(a, s);
+        DCRF_PERSIST_CASE(1)
+        DCRF_PERSIST_CASE(2)
+        DCRF_PERSIST_CASE(3)
+        DCRF_PERSIST_CASE(4)
+        DCRF_PERSIST_CASE(5)
+        DCRF_PERSIST_CASE(6)
+        DCRF_PERSIST_CASE(7)
+        DCRF_PERSIST_CASE(8)
+#undef DCRF_PERSIST_CASE
+    }
+    return false;
 }
 
 }  // namespace dcrf

@@ -134,6 +134,12 @@ class _Model(object):
         code = {"fma": 0, "reference": 1, "strict": 2, "auto": 3, 0: 0, 1: 1, 2: 2, 3: 3}[mode]
         _lib.check(self._lib.dcrf_set_option(self._h, 1, code))
 
+    def set_persistent(self, mode):
+        """One cooperative launch per inference(n) instead of a launch per phase: None / "auto" = by
+        problem size (default), False = never, True = whenever the model allows."""
+        code = {None: -1, "auto": -1, False: 0, True: 1}[mode]
+        _lib.check(self._lib.dcrf_set_option(self._h, 4, code))
+
     def arithmetic(self):
         """The mode this model resolved to: "fma", "reference" or "strict"."""
         m = C.c_int(0)
