@@ -554,7 +554,12 @@ def run_ours(args):
         dist.barrier()
     sw = None
     if not args.no_sweep:
-        sr = SW.run_sweep_device(SWEEP_IMAGES, SWEEP_LABELS, rank, world, batch=SWEEP_BATCH, device=local)
+        from wsss_analysis_b200.evaluation import CollectiveComm
+
+        comm = CollectiveComm(rank, world, local) if world > 1 else None   # ncclComm_t made through the C ABI
+        sr = SW.run_sweep_device(SWEEP_IMAGES, SWEEP_LABELS, rank, world, batch=SWEEP_BATCH, device=local, comm=comm)
+        if comm is not None:
+            comm.close()
         secs = torch.tensor([sr["seconds"]], dtype=torch.float64, device=dev)
         tot = torch.tensor([sr["pixels"], sr["images"]], dtype=torch.int64, device=dev)
         if world > 1:
@@ -566,7 +571,9 @@ def run_ours(args):
               "images": int(tot[1].item()), "seconds_max_over_ranks": float(secs.item()),
               "images_per_s": int(tot[1].item()) / float(secs.item()),
               "value": int(tot[0].item()) * 10 / float(secs.item()) / 1e6, "unit": UNIT,
-              "collective": "one all_reduce(SUM) of the (C+1, C) int64 confusion matrix (%s)" % ("NCCL, %d ranks" % world if world > 1 else "single rank: no-op"),
+              "collective": "one SUM all-reduce of the (C+1, C) int64 confusion matrix (%s)" % (
+                  "dcrf_confusion_allreduce = ncclAllReduce(int64) on a communicator of %d ranks made through the C ABI" % world
+                  if world > 1 else "single rank: no-op"),
               "confusion_sha256": hashlib.sha256(conf.tobytes()).hexdigest(), "pixels_counted": int(conf.sum()),
               "miou_irn": sr["miou_irn"], "miou_sec": sr["miou_sec"],
               "verified": "every rank's local matrix equals np.bincount of its downloaded label maps (bit-exact)"}

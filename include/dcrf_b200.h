@@ -124,11 +124,11 @@ enum { DCRF_ARITH_FMA = 0, DCRF_ARITH_REFERENCE = 1, DCRF_ARITH_STRICT = 2, DCRF
  * Host buffers should be page-locked, otherwise the copies are not asynchronous.  In this mode
  * dcrf_set_unary runs its upload and layout change on a separate per-thread stream, so the lattice
  * builds enqueued next overlap the upload; the handle's stream waits for it before the unary is read. */
-/* DCRF_OPT_PERSISTENT: dcrf_inference / dcrf_map / dcrf_run of a small problem (<= 400 000 pixels in the
- * handle: one VOC image, a training batch of 41x41 maps; DCRF_PERSISTENT_MAX_PIXELS overrides) run as ONE
- * cooperative launch with grid barriers between the phases instead of ~16 launches per iteration.
- * -1 (default) = by problem size, 0 = never, 1 = whenever the model allows (Potts terms, > 2 labels).
- * Same arithmetic, bit-identical marginals. */
+/* DCRF_OPT_PERSISTENT (experimental): run dcrf_inference / dcrf_map / dcrf_run as ONE cooperative launch
+ * with grid barriers between the phases instead of ~16 launches per iteration.  0 = never, 1 = whenever
+ * the model allows (Potts terms, > 2 labels), -1 (default) = for handles of at most
+ * DCRF_PERSISTENT_MAX_PIXELS pixels (environment; default 0 = never: on B200 the barriers cost as much
+ * as the launches they replace -- measured slower).  Same arithmetic, bit-identical marginals. */
 enum { DCRF_OPT_EXACT_ARITHMETIC = 1, DCRF_OPT_ASYNC_HOST = 2, DCRF_OPT_PERSISTENT = 4 };
 int dcrf_set_option(dcrf_t *h, int option, int value);
 int dcrf_get_arithmetic(dcrf_t *h, int *mode_out);
@@ -255,6 +255,19 @@ int dcrf_profile_read(dcrf_t *h, int kernel_class, int tag, double *total_ms, in
  * Predictions outside [0, C) are counted into *n_bad_pred (device int64, may be NULL). */
 int dcrf_confusion_accumulate(const int32_t *gt, const int32_t *pred, int64_t n, int n_classes,
                               int64_t *conf, int64_t *n_bad_pred, int device, void *stream);
+
+/* The one collective of the path: SUM all-reduce of the int64 confusion matrix over the ranks of a
+ * communicator (NCCL over NVLink / NVSwitch), in place, on `stream`.  Replaces the single-process
+ * accumulation of 03b_irn/step/eval_sem_seg.py:41-50 when the image list is striped over GPUs the way
+ * 03b_irn/step/cam_to_ir_label.py:114-117 stripes it over worker processes.  Integer addition is order
+ * independent: the result is bit-identical for every rank count.  `comm` is an ncclComm_t -- one the
+ * caller already has, or one made by dcrf_nccl_comm_create from a 128-byte ncclUniqueId that rank 0
+ * obtained with dcrf_nccl_unique_id and handed to the other ranks by any means (a file, MPI,
+ * torch.distributed).  NCCL is bound at run time (the libnccl.so.2 PyTorch ships, or DCRF_NCCL_LIB). */
+int dcrf_nccl_unique_id(void *id_out_128_bytes);
+int dcrf_nccl_comm_create(int n_ranks, int rank, const void *unique_id_128_bytes, int device, void **comm_out);
+int dcrf_nccl_comm_destroy(void *comm);
+int dcrf_confusion_allreduce(void *comm, int64_t *conf, int64_t count, int device, void *stream);
 
 /* ---- resizes either side of the path (device pointers) ---------------------------------------- */
 

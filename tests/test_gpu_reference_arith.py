@@ -235,8 +235,8 @@ def test_persistent_kernel_is_bit_identical_to_the_launch_per_phase_path(mode, s
 
 
 def test_persistent_batch_of_sec_maps_matches_oracle():
-    """BASELINE config 2: a batch of 41x41 maps (SEC.py:19) goes through the persistent kernel by
-    default; every map against the oracle."""
+    """BASELINE config 2: a batch of 41x41 maps (SEC.py:19) through the (opt-in) persistent kernel;
+    maps against the oracle."""
     from oracle import oracle as O
     from wsss_analysis_b200 import densecrf as G
     from wsss_analysis_b200 import synthetic as S
@@ -246,6 +246,7 @@ def test_persistent_batch_of_sec_maps_matches_oracle():
     Us = [S.random_unary(L, W * H, 50 + b) for b in range(B)]
     d = G.DenseCRFBatch([(W, H)] * B, L)
     d.set_arithmetic("strict")
+    d.set_persistent(True)
     d.setUnaryEnergy(Us)
     d.addPairwiseGaussian(sxy=3 / 12, compat=3)
     d.addPairwiseBilateral(sxy=80 / 12, srgb=13, rgbim=imgs, compat=10)

@@ -7,9 +7,9 @@ NAME=$1; shift
 OBJ=/tmp/dcrf_tune_$NAME
 mkdir -p $OBJ $ROOT/wsss_analysis_b200/csrc/tune
 cd $ROOT/wsss_analysis_b200/csrc
-for f in api lattice_build filter primitives confusion resize; do
+for f in api lattice_build filter primitives confusion resize collective; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c -o $OBJ/$f.o $f.cu &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tune/libdcrf_$NAME.so $OBJ/*.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tune/libdcrf_$NAME.so $OBJ/*.o -ldl
 echo built tune/libdcrf_$NAME.so

@@ -58,6 +58,10 @@ SIGNATURES = {
     "dcrf_resize_nearest_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp]),
     "dcrf_resize_bilinear_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "dcrf_confusion_accumulate": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp]),
+    "dcrf_nccl_unique_id": (_i, [_vp]),
+    "dcrf_nccl_comm_create": (_i, [_i, _i, _vp, _i, C.POINTER(_vp)]),
+    "dcrf_nccl_comm_destroy": (_i, [_vp]),
+    "dcrf_confusion_allreduce": (_i, [_vp, _vp, _i64, _i, _vp]),
 }
 
 _lib = None

@@ -177,6 +177,7 @@ struct Pairwise {
     Lattice lat;
     DevBuf<float> norm;    // [Ntot]; empty for NO_NORMALIZATION
     DevBuf<float> compat;  // diagonal: [Lp]; matrix: [Lp*Lp] zero padded
+    std::vector<float> compat_host;
     DevBuf<float> valA, valB;  // lattice value ping-pong, [M * Lp]
     int ntype = DCRF_NORMALIZE_SYMMETRIC, ktype = DCRF_DIAG_KERNEL;
     int compat_kind = DCRF_COMPAT_POTTS;
@@ -195,6 +196,7 @@ struct dcrf_handle {
     int L = 0, Lp = 0;
     bool has_geom = false;  // 2-D image geometry available (Gaussian / bilateral features)
     BatchGeom geom;
+    std::vector<int> ps32;
     DevBuf<int> d_w, d_h, d_pix_start;
     DevBuf<float> unary, Q;
     DevBuf<int> counters;  // row dispensers of the persistent mean-field kernel
@@ -308,7 +310,8 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     g.w.resize(B);
     g.h.resize(B);
     g.pix_start.assign(B + 1, 0);
-    std::vector<int> ps32(B + 1, 0);
+    std::vector<int> &ps32 = h->ps32;  // staging of an asynchronous upload: lives as long as the handle
+    ps32.assign(B + 1, 0);
     for (int b = 0; b < B; b++) {
         DCRF_REQUIRE(w[b] >= 1 && hgt[b] >= 1, DCRF_EINVAL, "image width/height must be >= 1");
         g.w[b] = w[b];
@@ -324,7 +327,6 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     DCRF_CUDA(copy_h2d(h->d_w.p, g.w.data(), sizeof(int) * B, h->stream));
     DCRF_CUDA(copy_h2d(h->d_h.p, g.h.data(), sizeof(int) * B, h->stream));
     DCRF_CUDA(copy_h2d(h->d_pix_start.p, ps32.data(), sizeof(int) * (B + 1), h->stream));
-    DCRF_CUDA(cudaStreamSynchronize(h->stream));  // host vectors above go out of scope
     g.d_w = h->d_w.p;
     g.d_h = h->d_h.p;
     g.d_pix_start = h->d_pix_start.p;
@@ -396,14 +398,16 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
     if (compat_kind == DCRF_COMPAT_POTTS) {
         p->potts_w = compat[0];
     } else if (compat_kind == DCRF_COMPAT_DIAGONAL) {
-        std::vector<float> c(Lp, 0.f);
+        std::vector<float> &c = p->compat_host;  // staging of an asynchronous upload
+        c.assign(Lp, 0.f);
         for (int l = 0; l < L; l++) c[l] = compat[l];
         p->compat.alloc(Lp, s);
         DCRF_CUDA(copy_h2d(p->compat.p, c.data(), sizeof(float) * Lp, s));
         DCRF_CUDA(cudaStreamSynchronize(s));
     } else {
         // [EXT] MatrixCompatibility stores 0.5 * (m + m^T)
-        std::vector<float> c((size_t)Lp * Lp, 0.f);
+        std::vector<float> &c = p->compat_host;
+        c.assign((size_t)Lp * Lp, 0.f);
         for (int a = 0; a < L; a++)
             for (int b = 0; b < L; b++) c[(size_t)a * Lp + b] = 0.5f * (compat[a * L + b] + compat[b * L + a]);
         p->compat.alloc((size_t)Lp * Lp, s);
@@ -553,16 +557,19 @@ void emit_labels(dcrf_handle *h, T *labels_out, int on_device) {
     }
 }
 
-// Small problems (one VOC image, a batch of SEC's 41x41 maps) run the whole of inference(n) as one
-// cooperative launch (filter.cu, mean_field_persistent_kernel); DCRF_PERSISTENT_MAX_PIXELS moves the
-// threshold (0 disables the path).
+// Opt-in: the whole of inference(n) as one cooperative launch (filter.cu,
+// mean_field_persistent_kernel).  Measured on B200 it LOSES against the launch-per-phase path it was
+// meant to beat (one VOC image: 2.54 vs 1.90 ms per step, 32 SEC maps: 1.41 vs 1.21 ms): ~9 grid
+// barriers per iteration cost as much as the launches they replace, and the fused kernel's 64-105
+// registers leave half the resident warps of the stand-alone latency-bound kernels.  Kept behind
+// DCRF_OPT_PERSISTENT = 1 (or DCRF_PERSISTENT_MAX_PIXELS > 0) with its bit-identity tests.
 bool try_persistent(dcrf_handle *h, int n_iter) {
     static const int64_t max_pix = [] {
         const char *e = getenv("DCRF_PERSISTENT_MAX_PIXELS");
-        return e ? (int64_t)atoll(e) : (int64_t)400000;
+        return e ? (int64_t)atoll(e) : (int64_t)0;  // default: off (measured slower on B200)
     }();
     const int n = (int)h->pw.size();
-    if (h->persistent == 0 || (h->persistent < 0 && h->geom.Ntot > max_pix)) return false;
+    if (h->persistent == 0 || (h->persistent < 0 && (max_pix <= 0 || h->geom.Ntot > max_pix))) return false;
     if (h->prof.on || h->L <= 2 || n == 0 || n_iter < 1 || h->Lp > 32) return false;
     int64_t max_rows = h->geom.Ntot;
     for (auto &p : h->pw) {

@@ -162,6 +162,10 @@ struct Lattice {
     int64_t M = 0;                 // total vertices
     int64_t E = 0;                 // Ntot * (d+1) entries
     std::vector<int64_t> vert_start; // host [B+1]
+    // host staging of small per-image tables uploaded asynchronously during the build (kept alive here
+    // instead of synchronising the stream before they go out of scope)
+    std::vector<int64_t> h_tab_start, h_tab2_start;
+    std::vector<int> h_tab_mask, h_tab2_mask;
     DevBuf<int32_t> offset;        // [E] vertex id of entry e = p*(d+1)+r
     DevBuf<float> bary;            // [E]
     DevBuf<int2> neigh;            // [(d+1) * M] (n1, n2), -1 = absent

@@ -396,8 +396,10 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     prof.reset(new ProfScope(DCRF_K_BUILD_HASH, D, s));
     // per-image table regions: capacity = pow2 >= 1.25 * N_b * (d+1) entries, i.e. a load factor of at
     // most 0.8 in the worst case of all-distinct keys (natural images: M ~ 0.1 E, load < 0.1)
-    std::vector<int64_t> tab_start(B + 1, 0);
-    std::vector<int> tab_mask(B);
+    std::vector<int64_t> &tab_start = out.h_tab_start;
+    std::vector<int> &tab_mask = out.h_tab_mask;
+    tab_start.assign(B + 1, 0);
+    tab_mask.assign(B, 0);
     for (int b = 0; b < B; b++) {
         int64_t need = (5 * (g.pix_start[b + 1] - g.pix_start[b]) * d1 + 3) / 4;
         int64_t cap = 64;
@@ -455,8 +457,10 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     // Neighbour look-ups go through a second, COMPACT table of vertex ids (capacity = pow2 >= 2 M_b per
     // image, ~1 MB per VOC image: the batch's tables stay L2 resident), instead of the insertion table
     // that is sized for the worst case M = E (16 MB per image, every probe a DRAM access).
-    std::vector<int64_t> tab2_start(B + 1, 0);
-    std::vector<int> tab2_mask(B);
+    std::vector<int64_t> &tab2_start = out.h_tab2_start;
+    std::vector<int> &tab2_mask = out.h_tab2_mask;
+    tab2_start.assign(B + 1, 0);
+    tab2_mask.assign(B, 0);
     for (int b = 0; b < B; b++) {
         const int64_t need = 2 * (int64_t)(h_vs[b + 1] - h_vs[b]);
         int64_t cap = 64;
@@ -482,7 +486,6 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
         M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
     DCRF_LAUNCHED();
-    DCRF_CUDA(cudaStreamSynchronize(s));  // tab2_* host vectors are read by the async copies above
 
     // transposed incidence rows: stable sort of entries by vertex id
     prof.reset();

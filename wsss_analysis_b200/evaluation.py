@@ -14,9 +14,60 @@ to a single-process NumPy bincount.  PyTorch is used only to own the device buff
 `torch.distributed` collective (NCCL on GPUs; gloo in the CPU tests, which exercise the host logic
 with host-side counting disabled -- the counting itself always runs in the CUDA kernel).
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _lib
+
+
+class CollectiveComm(object):
+    """An NCCL communicator made through the C ABI (dcrf_nccl_comm_create): what the C-level
+    collective `dcrf_confusion_allreduce` runs on.  The 128-byte ncclUniqueId is generated on rank 0 and
+    handed to the other ranks either by the caller (`unique_id=`, any transport) or, by default,
+    through `torch.distributed.broadcast_object_list` of an already initialised process group -- the
+    only use of PyTorch here is that hand-off."""
+
+    def __init__(self, rank, world_size, device, unique_id=None, group=None):
+        self._lib = _lib.load()
+        self.rank, self.world_size, self.device = int(rank), int(world_size), int(device)
+        if unique_id is None:
+            import torch.distributed as dist
+
+            obj = [self.new_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            unique_id = obj[0]
+        assert len(unique_id) == 128
+        comm = C.c_void_p()
+        _lib.check(self._lib.dcrf_nccl_comm_create(self.world_size, self.rank, unique_id, self.device, C.byref(comm)))
+        self._comm = comm
+
+    @staticmethod
+    def new_unique_id():
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().dcrf_nccl_unique_id(buf))
+        return bytes(buf.raw)
+
+    def all_reduce_i64(self, tensor, stream=None):
+        """In-place SUM all-reduce of an int64 CUDA tensor on `stream` (default: torch's current stream)."""
+        import torch
+
+        assert tensor.is_cuda and tensor.dtype == torch.int64 and tensor.is_contiguous()
+        if stream is None:
+            stream = torch.cuda.current_stream(tensor.device).cuda_stream
+        _lib.check(self._lib.dcrf_confusion_allreduce(self._comm, tensor.data_ptr(), tensor.numel(),
+                                                      tensor.device.index, stream))
+
+    def close(self):
+        comm, self._comm = self._comm, None
+        if comm:
+            _lib.check(self._lib.dcrf_nccl_comm_destroy(comm))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ConfusionAccumulator(object):
@@ -59,10 +110,16 @@ class ConfusionAccumulator(object):
 
         torch.cuda.synchronize(self.device)
 
-    def all_reduce(self, group=None):
-        """Sum over all ranks (NCCL over NVLink on GPUs).  No-op without an initialised process group."""
+    def all_reduce(self, group=None, comm=None):
+        """Sum over all ranks (NCCL over NVLink on GPUs).  comm: a CollectiveComm -> the C-level
+        collective (dcrf_confusion_allreduce, ncclAllReduce int64 SUM); otherwise
+        torch.distributed.all_reduce of the initialised process group (no-op without one)."""
         import torch.distributed as dist
 
+        if comm is not None:
+            comm.all_reduce_i64(self.conf)
+            comm.all_reduce_i64(self.bad)
+            return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.conf, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(self.bad, op=dist.ReduceOp.SUM, group=group)

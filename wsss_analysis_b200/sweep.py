@@ -72,7 +72,7 @@ def run_sweep(items, n_labels, rank=0, world_size=1, batch=16, crf=VOC_CRF, devi
 
 
 def run_sweep_device(n_items, n_labels, rank=0, world_size=1, batch=32, crf=VOC_CRF, device=0, all_reduce=True,
-                     verify=True, seed=0):
+                     verify=True, seed=0, comm=None):
     """The same sweep with inputs synthesised on the GPU (`synthetic.torch_sweep_item`) and handed over
     as device tensors: unaries, images, label maps and the confusion matrix never touch the host.
     Image i goes to rank i mod world_size (`split_dataset` striding, cam_to_ir_label.py:114-117).
@@ -111,7 +111,7 @@ def run_sweep_device(n_items, n_labels, rank=0, world_size=1, batch=32, crf=VOC_
     if verify and not np.array_equal(acc.result(), ref):
         raise AssertionError("GPU confusion matrix differs from np.bincount on rank %d" % rank)
     if all_reduce:
-        acc.all_reduce()
+        acc.all_reduce(comm=comm)   # comm: evaluation.CollectiveComm -> dcrf_confusion_allreduce (C ABI)
     conf = acc.result()
     return dict(confusion=conf, miou_irn=iou_irn(conf)[1], miou_sec=iou_sec(conf)[1], images=len(mine),
                 pixels=pixels, seconds=seconds, verified=bool(verify), bad_predictions=acc.bad_predictions())
