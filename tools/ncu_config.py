@@ -15,13 +15,19 @@ U = torch.from_numpy(np.concatenate([u.ravel() for u in unaries])).to(dev)
 I = torch.from_numpy(np.concatenate([im.ravel() for im in imgs])).to(dev)
 Q = torch.empty(bench.npix(cfg) * cfg["L"], dtype=torch.float32, device=dev)
 torch.cuda.synchronize()
+import time
 for it in range(steps):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     crf = G.DenseCRFBatch(cfg["sizes"], cfg["L"], device=0)
     if len(sys.argv) > 3:
         crf.set_arithmetic(sys.argv[3])
     crf.setUnaryEnergy(U)
+    t1 = time.perf_counter()
     crf.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
+    torch.cuda.synchronize(); t2 = time.perf_counter()
     crf.addPairwiseBilateral(sxy=cfg["b_sxy"], srgb=cfg["b_srgb"], rgbim=I, compat=cfg["b_compat"])
+    torch.cuda.synchronize(); t3 = time.perf_counter()
     crf.inference_device(cfg["iters"], out=Q)
+    torch.cuda.synchronize(); t4 = time.perf_counter()
     crf.close()
-    print("step", it, "done", float(Q[:100].sum()), flush=True)
+    print("step %d: create+unary %.2f gauss %.2f bilat %.2f infer %.2f ms" % (it, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3), flush=True)

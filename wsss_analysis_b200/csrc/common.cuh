@@ -166,6 +166,7 @@ struct Lattice {
     // instead of synchronising the stream before they go out of scope)
     std::vector<int64_t> h_tab_start, h_tab2_start;
     std::vector<int> h_tab_mask, h_tab2_mask;
+    std::vector<int32_t> h_seg, h_tile;
     DevBuf<int32_t> offset;        // [E] vertex id of entry e = p*(d+1)+r
     DevBuf<float> bary;            // [E]
     DevBuf<int2> neigh;            // [(d+1) * M] (n1, n2), -1 = absent
@@ -287,7 +288,8 @@ void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t
 // Returns 0 when the sorted pairs ended in keys_a / vals_a, 1 when they ended in keys_b / vals_b.
 int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
                                const std::vector<int64_t> &seg_start, const int32_t *d_key_base,
-                               int local_bits, cudaStream_t s);
+                               int local_bits, cudaStream_t s, std::vector<int32_t> &h_seg,
+                               std::vector<int32_t> &h_tile);
 int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
                       int64_t n, int bits, cudaStream_t s);
 

@@ -302,6 +302,62 @@ __global__ void __launch_bounds__(kThreads) compact_insert_kernel(
     while (atomicCAS(&tab[h], -1, (int32_t)v) != -1) h = (h + 1) & mask;
 }
 
+// Wide-slot form of the compact table (d <= 6: the key fits three ints): a slot is (key.x, key.y,
+// key.z, vertex id), so a probe is ONE 16-byte read and never touches vkeys[] -- the narrow table
+// costs a 4-byte slot read plus a dependent 16-byte vkeys gather per probed slot.  Keys are unique, so
+// an insert claims the id word with a CAS and then stores its key words; the look-ups run in a later
+// kernel.  (neighbour_kernel<5>, VOC batch of 32: 485 us with narrow slots.)
+__global__ void __launch_bounds__(kThreads) compact_insert_wide_kernel(
+    int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
+    const int *__restrict__ tab_mask, const int4 *__restrict__ vkeys, int4 *table) {
+    const int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (v >= M) return;
+    const int b = find_image(vert_start, B, v);
+    int4 *tab = table + tab_start[b];
+    const uint32_t mask = (uint32_t)tab_mask[b];
+    const int4 k = vkeys[v];
+    uint32_t h = key_hash(k) & mask;
+    while (atomicCAS(&tab[h].w, -1, (int32_t)v) != -1) h = (h + 1) & mask;
+    int *slot = reinterpret_cast<int *>(&tab[h]);
+    slot[0] = k.x;
+    slot[1] = k.y;
+    slot[2] = k.z;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) neighbour_wide_kernel(
+    int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
+    const int *__restrict__ tab_mask, const int4 *__restrict__ table, const int4 *__restrict__ vkeys,
+    int2 *__restrict__ neigh) {
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= M * (D + 1)) return;
+    const int j = (int)(t / M);
+    const int64_t v = t - (int64_t)j * M;
+    const int b = find_image(vert_start, B, v);
+    const int4 *tab = table + tab_start[b];
+    const uint32_t mask = (uint32_t)tab_mask[b];
+    const int4 kv = vkeys[v];
+    const short *key = reinterpret_cast<const short *>(&kv);
+    short nk[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k < D) nk[k] = (short)(key[k] + ((k == j) ? D : -1));
+        else nk[k] = 0;
+    }
+    const int4 pk = pack_key(nk);
+    uint32_t h = key_hash(pk) & mask;
+    int found = -1;
+    for (;;) {
+        const int4 cur = __ldg(tab + h);
+        if (cur.w < 0) break;
+        if (cur.x == pk.x && cur.y == pk.y && cur.z == pk.z) { found = cur.w; break; }
+        h = (h + 1) & mask;
+    }
+    int *nflat = reinterpret_cast<int *>(neigh + (int64_t)j * M);
+    nflat[2 * v] = found;
+    if (found >= 0) nflat[2 * (int64_t)found + 1] = (int)v;
+}
+
 // vert_start[b] = number of first occurrences before image b's first entry
 __global__ void vert_start_kernel(const int *__restrict__ pix_start, int B, int d1,
                                   const int32_t *__restrict__ scanned, int32_t *__restrict__ vert_start) {
@@ -470,22 +526,33 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     }
     DevBuf<int64_t> d_tab2_start;
     DevBuf<int> d_tab2_mask;
-    DevBuf<int32_t> table2;
     d_tab2_start.alloc(B + 1, s);
     d_tab2_mask.alloc(B, s);
-    table2.alloc(tab2_start[B], s);
     DCRF_CUDA(copy_h2d(d_tab2_start.p, tab2_start.data(), sizeof(int64_t) * (B + 1), s));
     DCRF_CUDA(copy_h2d(d_tab2_mask.p, tab2_mask.data(), sizeof(int) * B, s));
-    DCRF_CUDA(cudaMemsetAsync(table2.p, 0xFF, sizeof(int32_t) * tab2_start[B], s));
-    compact_insert_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
-                                                                    d_tab2_mask.p, vkeys4, table2.p);
-    DCRF_LAUNCHED();
-
     out.neigh.alloc((size_t)M * d1, s);
     DCRF_CUDA(cudaMemsetAsync(out.neigh.p, 0xFF, sizeof(int2) * M * d1, s));
-    neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
-        M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
-    DCRF_LAUNCHED();
+    if (D <= 6) {  // wide slots: (key.x, key.y, key.z, id); 0xFF fill = id -1 = empty
+        DevBuf<int4> table2;
+        table2.alloc(tab2_start[B], s);
+        DCRF_CUDA(cudaMemsetAsync(table2.p, 0xFF, sizeof(int4) * tab2_start[B], s));
+        compact_insert_wide_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
+                                                                             d_tab2_mask.p, vkeys4, table2.p);
+        DCRF_LAUNCHED();
+        neighbour_wide_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
+            M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
+        DCRF_LAUNCHED();
+    } else {
+        DevBuf<int32_t> table2;
+        table2.alloc(tab2_start[B], s);
+        DCRF_CUDA(cudaMemsetAsync(table2.p, 0xFF, sizeof(int32_t) * tab2_start[B], s));
+        compact_insert_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
+                                                                        d_tab2_mask.p, vkeys4, table2.p);
+        DCRF_LAUNCHED();
+        neighbour_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
+            M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
+        DCRF_LAUNCHED();
+    }
 
     // transposed incidence rows: stable sort of entries by vertex id
     prof.reset();
@@ -498,7 +565,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     for (int b = 0; b < B; b++) max_mb = std::max<int64_t>(max_mb, out.vert_start[b + 1] - out.vert_start[b]);
     int bits = 1;
     while (((int64_t)1 << bits) < max_mb) bits++;
-    const int in_b = segmented_radix_sort_pairs(ka.p, va.p, kb.p, vb.p, ent_start, d_vert_start.p, bits, s);
+    const int in_b = segmented_radix_sort_pairs(ka.p, va.p, kb.p, vb.p, ent_start, d_vert_start.p, bits, s, out.h_seg, out.h_tile);
     const uint32_t *sk = in_b ? kb.p : ka.p, *sv = in_b ? vb.p : va.p;
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_CSR, D, s));
