@@ -79,6 +79,9 @@ int dcrf_stream_create(int device, void **stream_out);
  * max).  dcrf_trim_memory() synchronises the current device and returns all cached, unused memory
  * of every pool to the driver. */
 int dcrf_trim_memory(void);
+/* free / total device memory, counting the unused memory cached in the library's pools as free (the
+ * batching wrappers size their handles with it) */
+int dcrf_mem_info(int device, int64_t *free_bytes, int64_t *total_bytes);
 int dcrf_stream_destroy(void *stream);
 
 /* Replaces `dcrf.DenseCRF2D(w, h, nlabels)` (03c_hsn/utilities.py:427; width first).

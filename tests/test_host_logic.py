@@ -166,6 +166,33 @@ def test_wrapper_batches_are_chunked_below_the_int32_entry_limit(monkeypatch):
     assert wsss._chunks(range(5), [10] * 5) == [[0, 1], [2, 3], [4]]
     assert wsss._chunks([0, 2, 4], [30, 1, 2, 3, 40]) == [[0], [2], [4]]  # an over-size image runs alone
     assert wsss._chunks([], []) == []
+    assert wsss._chunks(range(6), [1] * 6, max_pixels=4) == [[0, 1, 2, 3], [4, 5]]      # memory budget
+    monkeypatch.setattr(wsss, "_MAX_BATCH_IMAGES", 2)                                     # launch-grid bound
+    assert wsss._chunks(range(5), [1] * 5, max_pixels=100) == [[0, 1], [2, 3], [4]]
+    assert wsss._bytes_per_pixel(21) > 21 * 4 * 4 and wsss._bytes_per_pixel(29) > wsss._bytes_per_pixel(21)
+
+
+def test_wrapper_chunks_are_halved_when_the_device_runs_out_of_memory():
+    """a chunk whose handle raises MemoryError (DCRF_ENOMEM) is split and retried; every
+    index is still processed exactly once, in order; a single image that does not fit re-raises."""
+    seen = []
+
+    def fn(idx):
+        if len(idx) > 2:
+            raise MemoryError("pretend the lattices were denser than estimated")
+        seen.append(list(idx))
+
+    wsss._run_chunked(range(7), [1] * 7, 21, None, fn, budget=100)
+    assert seen == [[0], [1, 2], [3, 4], [5, 6]] and sum(seen, []) == list(range(7))
+
+    def always(idx):
+        raise MemoryError("too large")
+
+    try:
+        wsss._run_chunked(range(2), [1, 1], 21, None, always, budget=100)
+        raise AssertionError("expected MemoryError")
+    except MemoryError:
+        pass
 
 
 def test_pipeline_sub_batch_views():

@@ -23,13 +23,19 @@ CASES = {
     "adp_func": (48, 48, 5, 5, 3, 40, 10, 4, 25, "histo", 3),                # SEC.py:29-30
     "hsn_voc": (56, 56, 6, 10, 3 / 2, 3, 80 / 2, 13, 10, "natural", 4),      # 03c_hsn/demo.py:159
     "irn_label": (60, 44, 4, 10, 3, 3, 50, 5, 10, "iid", 5),                 # IRN_CRF_CONFIG
+    # HSN VOC-M7 (03c_hsn/demo.py:161): sxy 3/12/4 and 80/12/4 -- the largest lattice coordinates in the
+    # tree (x / 0.0625 at 224 px); a 224-wide strip keeps the fixture small
+    "hsn_voc_m7": (224, 16, 8, 10, 3 / 12 / 4, 3, 80 / 12 / 4, 13, 10, "natural", 6),
 }
 
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])   # optional: regenerate just the named fixtures
     for name, (W, H, L, n, gs, gc, bs, srgb, bc, kind, seed) in CASES.items():
+        if only and name not in only:
+            continue
         img = getattr(S, kind + "_image")(H, W, seed)
         U = S.random_unary(L, W * H, seed)
         d = O.DenseCRF2D(W, H, L)

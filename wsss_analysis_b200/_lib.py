@@ -20,6 +20,7 @@ SIGNATURES = {
     "dcrf_launch_count": (_i64, []),
     "dcrf_copy_count": (None, [C.POINTER(_i64), C.POINTER(_i64)]),
     "dcrf_trim_memory": (_i, []),
+    "dcrf_mem_info": (_i, [_i, C.POINTER(_i64), C.POINTER(_i64)]),
     "dcrf_stream_create": (_i, [_i, C.POINTER(_vp)]),
     "dcrf_stream_destroy": (_i, [_vp]),
     "dcrf_create": (_i, [_i, _i, _i, _i, _vp, C.POINTER(_vp)]),

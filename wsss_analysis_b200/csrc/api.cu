@@ -673,6 +673,32 @@ void dcrf_destroy(dcrf_t *h) {
     delete h;
 }
 
+int dcrf_mem_info(int device, int64_t *free_bytes, int64_t *total_bytes) {
+    return guarded([&] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            throw Error{DCRF_ECUDA, "no CUDA device: dcrf_b200 has no CPU fallback"};
+        if (device < 0) DCRF_CUDA(cudaGetDevice(&device));
+        DCRF_REQUIRE(device < ndev, DCRF_EINVAL, "device index out of range");
+        DeviceGuard guard(device);
+        size_t f = 0, t = 0;
+        DCRF_CUDA(cudaMemGetInfo(&f, &t));
+        // memory cached by the library's own pools is reusable by the next handle: count it as free
+        {
+            std::lock_guard<std::mutex> lock(g_pool_mu);
+            for (auto &kv : g_pools) {
+                if (kv.first.first != device) continue;
+                uint64_t reserved = 0, used = 0;
+                cudaMemPoolGetAttribute(kv.second, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(kv.second, cudaMemPoolAttrUsedMemCurrent, &used);
+                if (reserved > used) f += (size_t)(reserved - used);
+            }
+        }
+        if (free_bytes) *free_bytes = (int64_t)f;
+        if (total_bytes) *total_bytes = (int64_t)t;
+    });
+}
+
 int dcrf_trim_memory(void) {
     return guarded([&] {
         DCRF_CUDA(cudaDeviceSynchronize());

@@ -284,12 +284,14 @@ void launch_slice_pairwise_only(const SliceTerm &t, float *out, int64_t Ntot, in
 // ---------------------------------------------------------------------------------------------
 // out[i] = exclusive prefix sum of in[0..i), out[n] = total.  in/out may alias.  int32.
 void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
+// Stable LSD radix sort of interleaved (key, value) pairs inside consecutive segments, by
+// (key - key_base[segment]) on `local_bits` bits.  Returns 0 when the sorted pairs ended in pairs_a, 1
+// when they ended in pairs_b.  h_seg / h_tile: caller-owned staging of two small uploads.
+int segmented_radix_sort_pairs(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
+                               const int32_t *d_key_base, int local_bits, cudaStream_t s,
+                               std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile);
 // stable LSD radix sort of (key, value) pairs on the low `bits` bits of key (8 bits per pass).
 // Returns 0 when the sorted pairs ended in keys_a / vals_a, 1 when they ended in keys_b / vals_b.
-int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
-                               const std::vector<int64_t> &seg_start, const int32_t *d_key_base,
-                               int local_bits, cudaStream_t s, std::vector<int32_t> &h_seg,
-                               std::vector<int32_t> &h_tile);
 int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
                       int64_t n, int bits, cudaStream_t s);
 

@@ -271,8 +271,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
     const int32_t *__restrict__ slot_of, const int32_t *__restrict__ scanned,
     const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
-    int32_t *__restrict__ offset, int4 *__restrict__ vkeys,
-    uint32_t *__restrict__ sort_keys, uint32_t *__restrict__ sort_vals) {
+    int32_t *__restrict__ offset, int4 *__restrict__ vkeys, uint2 *__restrict__ sort_pairs) {
     const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (e >= E) return;
     const int64_t gp = e / (D + 1);
@@ -280,8 +279,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     const int32_t rep = table[tab_start[b] + slot_of[e]];
     const int32_t id = scanned[rep];
     offset[e] = id;
-    sort_keys[e] = (uint32_t)id;  // (vertex, entry) pairs for the CSR sort (K6)
-    sort_vals[e] = (uint32_t)e;
+    sort_pairs[e] = make_uint2((uint32_t)id, (uint32_t)e);  // (vertex, entry) pairs for the CSR sort (K6)
     if (rep == (int32_t)e) {
         short key[8];
         entry_key<D>(rec_rem[gp], rec_rank[gp], (int)(e - gp * (D + 1)), key);
@@ -405,16 +403,15 @@ __global__ void __launch_bounds__(kThreads) neighbour_kernel(
 
 // K6 epilogue: sorted (vertex, entry) pairs -> CSR rows
 __global__ void __launch_bounds__(kThreads) csr_finalize_kernel(
-    const uint32_t *__restrict__ skeys, const uint32_t *__restrict__ svals,
-    const float *__restrict__ bary, int d1, int64_t E, int64_t M, int32_t *__restrict__ csr_start,
-    int32_t *__restrict__ csr_pix, float *__restrict__ csr_w) {
+    const uint2 *__restrict__ sorted, const float *__restrict__ bary, int d1, int64_t E, int64_t M,
+    int32_t *__restrict__ csr_start, int32_t *__restrict__ csr_pix, float *__restrict__ csr_w) {
     const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (s >= E) return;
-    const uint32_t v = skeys[s];
-    const uint32_t e = svals[s];
+    const uint2 ve = sorted[s];
+    const uint32_t v = ve.x, e = ve.y;
     csr_pix[s] = (int32_t)(e / (uint32_t)d1);
     csr_w[s] = bary[e];
-    if (s == 0 || skeys[s - 1] != v) csr_start[v] = (int32_t)s;
+    if (s == 0 || sorted[s - 1].x != v) csr_start[v] = (int32_t)s;
     if (s == E - 1) csr_start[M] = (int32_t)E;
 }
 
@@ -503,10 +500,10 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     out.offset.alloc(E, s);
     out.vkeys.alloc((size_t)M * 8, s);
     int4 *vkeys4 = reinterpret_cast<int4 *>(out.vkeys.p);
-    DevBuf<uint32_t> ka, va, kb, vb;
-    ka.alloc(E, s); va.alloc(E, s);
+    DevBuf<uint2> pa, pb;  // interleaved (vertex, entry) pairs: one 8-byte scatter per pair and pass
+    pa.alloc(E, s);
     assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
-                                             rec_rem.p, rec_rank.p, out.offset.p, vkeys4, ka.p, va.p);
+                                             rec_rem.p, rec_rank.p, out.offset.p, vkeys4, pa.p);
     DCRF_LAUNCHED();
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_NEIGH, D, s));
@@ -557,7 +554,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     // transposed incidence rows: stable sort of entries by vertex id
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_SORT, D, s));
-    kb.alloc(E, s); vb.alloc(E, s);
+    pb.alloc(E, s);
     // per-image segments: keys local to an image need fewer radix passes than batch-global ids
     int64_t max_mb = 1;
     std::vector<int64_t> ent_start(B + 1);
@@ -565,15 +562,15 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     for (int b = 0; b < B; b++) max_mb = std::max<int64_t>(max_mb, out.vert_start[b + 1] - out.vert_start[b]);
     int bits = 1;
     while (((int64_t)1 << bits) < max_mb) bits++;
-    const int in_b = segmented_radix_sort_pairs(ka.p, va.p, kb.p, vb.p, ent_start, d_vert_start.p, bits, s, out.h_seg, out.h_tile);
-    const uint32_t *sk = in_b ? kb.p : ka.p, *sv = in_b ? vb.p : va.p;
+    const int in_b = segmented_radix_sort_pairs(pa.p, pb.p, ent_start, d_vert_start.p, bits, s, out.h_seg, out.h_tile);
+    const uint2 *sorted = in_b ? pb.p : pa.p;
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_CSR, D, s));
     out.csr_start.alloc(M + 1, s);
     out.csr_pix.alloc(E, s);
     out.csr_w.alloc(E, s);
-    csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(sk, sv, out.bary.p, d1, E, M, out.csr_start.p,
-                                                out.csr_pix.p, out.csr_w.p);
+    csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(sorted, out.bary.p, d1, E, M, out.csr_start.p, out.csr_pix.p,
+                                                out.csr_w.p);
     DCRF_LAUNCHED();
 }
 

@@ -230,7 +230,7 @@ __device__ __forceinline__ int seg_of_tile(const SegInfo &si, int tile) {
     return lo;
 }
 
-__global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint32_t *__restrict__ keys,
+__global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint2 *__restrict__ pairs,
                                                                       int32_t *__restrict__ hist, SegInfo si,
                                                                       int shift, int digit_bits) {
     __shared__ int h[kSegMaxRadix];
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint
 #pragma unroll
     for (int i = 0; i < kSortRounds; i++) {
         const int64_t idx = base + (int64_t)i * kSortThreads + threadIdx.x;
-        if (idx < end) atomicAdd(&h[((keys[idx] - kb) >> shift) & (radix - 1)], 1);
+        if (idx < end) atomicAdd(&h[((pairs[idx].x - kb) >> shift) & (radix - 1)], 1);
     }
     __syncthreads();
     int32_t *hs = hist + (int64_t)radix * si.tile_base[seg];
@@ -254,9 +254,8 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint
 }
 
 __global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
-    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-    const int32_t *__restrict__ hist_scanned, SegInfo si, int shift, int digit_bits) {
+    const uint2 *__restrict__ pairs_in, uint2 *__restrict__ pairs_out, const int32_t *__restrict__ hist_scanned,
+    SegInfo si, int shift, int digit_bits) {
     __shared__ int cnt[kSortWarps][kSegMaxRadix];
     const int radix = 1 << digit_bits;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,13 +267,13 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
     const int64_t end = si.seg_start[seg + 1];
     const uint32_t kb = (uint32_t)si.key_base[seg];
     const int64_t wbase = (int64_t)si.seg_start[seg] + (int64_t)t * kSortTile + (int64_t)warp * kSortWarpChunk;
-    uint32_t k[kSortRounds];
+    uint2 k[kSortRounds];
 #pragma unroll
     for (int r = 0; r < kSortRounds; r++) {
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < end;
-        k[r] = valid ? keys_in[idx] : 0u;
-        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        k[r] = valid ? pairs_in[idx] : make_uint2(0u, 0u);
+        const int digit = valid ? (int)(((k[r].x - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[warp][digit] += __popc(peers);
         __syncwarp();
@@ -295,130 +294,21 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
     for (int r = 0; r < kSortRounds; r++) {
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < end;
-        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        const int digit = valid ? (int)(((k[r].x - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         const int rank = __popc(peers & ((1u << lane) - 1));
-        if (valid) {
-            const int pos = cnt[warp][digit] + rank;
-            keys_out[pos] = k[r];
-            vals_out[pos] = vals_in[idx];
-        }
+        if (valid) pairs_out[cnt[warp][digit] + rank] = k[r];  // one 8-byte scatter per pair
         __syncwarp();
         if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
         __syncwarp();
     }
 }
 
-
-// Same pass with the tile's pairs first ordered by digit in SHARED memory and then written out in that
-// order: pairs of one digit leave the CTA as one contiguous run (coalesced 32-byte sectors) instead of
-// 4096 individual 4-byte scatters (8x write amplification at sector granularity).  Measured on B200, VOC
-// batch of 32 (36 M pairs, 9-bit digits): low-digit pass 482 -> see profiles/README.md.
-// dynamic shared memory: int cnt[kSortWarps][radix], lstart[radix], gbase[radix]; uint32 skey[tile], sval[tile]
-__global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_staged_kernel(
-    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-    const int32_t *__restrict__ hist_scanned, SegInfo si, int shift, int digit_bits) {
-    extern __shared__ int sm[];
-    const int radix = 1 << digit_bits;
-    int *cnt = sm;                          // [kSortWarps][radix]
-    int *lstart = cnt + kSortWarps * radix; // [radix]
-    int *gbase = lstart + radix;            // [radix]
-    uint32_t *skey = reinterpret_cast<uint32_t *>(gbase + radix);
-    uint32_t *sval = skey + kSortTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kSortWarps * radix; i += kSortThreads) cnt[i] = 0;
-    __syncthreads();
-    const int seg = seg_of_tile(si, blockIdx.x);
-    const int t = blockIdx.x - si.tile_base[seg];
-    const int tiles = si.tile_base[seg + 1] - si.tile_base[seg];
-    const int64_t end = si.seg_start[seg + 1];
-    const uint32_t kb = (uint32_t)si.key_base[seg];
-    const int64_t tbase = (int64_t)si.seg_start[seg] + (int64_t)t * kSortTile;
-    const int64_t wbase = tbase + (int64_t)warp * kSortWarpChunk;
-    const int n_tile = (int)min((int64_t)kSortTile, end - tbase);
-    int *wc = cnt + warp * radix;
-    uint32_t k[kSortRounds];
-#pragma unroll
-    for (int r = 0; r < kSortRounds; r++) {
-        const int64_t idx = wbase + r * 32 + lane;
-        const bool valid = idx < end;
-        k[r] = valid ? keys_in[idx] : 0u;
-        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (valid && (peers & ((1u << lane) - 1)) == 0) wc[digit] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    // tile-local start of every digit (exclusive scan of the digit totals), per-warp local starts, and
-    // the digit's global output position for this tile
-    {
-        const int per = radix / kSortThreads > 0 ? radix / kSortThreads : 1;  // consecutive digits per thread
-        const int d0 = threadIdx.x * per;
-        int tot[4] = {0, 0, 0, 0};
-        int mine = 0;
-        for (int j = 0; j < per; j++) {
-            const int digit = d0 + j;
-            if (digit < radix) {
-                int c = 0;
-#pragma unroll
-                for (int w = 0; w < kSortWarps; w++) c += cnt[w * radix + digit];
-                tot[j] = c;
-                mine += c;
-            }
-        }
-        int total;
-        int run = block_exclusive_scan(mine, &total);
-        for (int j = 0; j < per; j++) {
-            const int digit = d0 + j;
-            if (digit < radix) {
-                lstart[digit] = run;
-                gbase[digit] = hist_scanned[(int64_t)radix * si.tile_base[seg] + (int64_t)digit * tiles + t];
-                int wrun = run;
-#pragma unroll
-                for (int w = 0; w < kSortWarps; w++) {
-                    const int c = cnt[w * radix + digit];
-                    cnt[w * radix + digit] = wrun;
-                    wrun += c;
-                }
-                run += tot[j];
-            }
-        }
-    }
-    __syncthreads();
-    // stable placement into the staging area, warp chunk walked in order
-#pragma unroll
-    for (int r = 0; r < kSortRounds; r++) {
-        const int64_t idx = wbase + r * 32 + lane;
-        const bool valid = idx < end;
-        const int digit = valid ? (int)(((k[r] - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        const int rank = __popc(peers & ((1u << lane) - 1));
-        if (valid) {
-            const int lp = wc[digit] + rank;
-            skey[lp] = k[r];
-            sval[lp] = vals_in[idx];
-        }
-        __syncwarp();
-        if (valid && rank == 0) wc[digit] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_tile; i += kSortThreads) {
-        const uint32_t key = skey[i];
-        const int digit = (int)(((key - kb) >> shift) & (radix - 1));
-        const int pos = gbase[digit] + (i - lstart[digit]);
-        keys_out[pos] = key;
-        vals_out[pos] = sval[i];
-    }
-}
-
 }  // namespace
 
-int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
-                               const std::vector<int64_t> &seg_start, const int32_t *d_key_base,
-                               int local_bits, cudaStream_t s, std::vector<int32_t> &h_seg,
-                               std::vector<int32_t> &h_tile) {
+int segmented_radix_sort_pairs(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
+                               const int32_t *d_key_base, int local_bits, cudaStream_t s,
+                               std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile) {
     const int S = (int)seg_start.size() - 1;
     if (S <= 0 || seg_start[S] <= 0) return 0;
     int passes = (local_bits + kSegMaxDigitBits - 1) / kSegMaxDigitBits;
@@ -437,30 +327,17 @@ int segmented_radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *key
     DCRF_CUDA(copy_h2d(d_tile.p, h_tile.data(), sizeof(int32_t) * (S + 1), s));
     hist.alloc((size_t)radix * total_tiles + 1, s);
     SegInfo si{d_seg.p, d_key_base, d_tile.p, S};
-    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+    uint2 *ki = pairs_a, *ko = pairs_b;
     for (int p = 0; p < passes; p++) {
         const int shift = p * digit_bits;
         seg_radix_hist_kernel<<<total_tiles, kSortThreads, 0, s>>>(ki, hist.p, si, shift, digit_bits);
         DCRF_LAUNCHED();
         scan_rec(hist.p, hist.p, (int64_t)radix * total_tiles, false, s);
-        if (radix >= kSortThreads) {
-            const size_t smem = sizeof(int) * ((size_t)kSortWarps * radix + 2 * radix) + sizeof(uint32_t) * 2 * kSortTile;
-            static bool attr_set = false;
-            if (!attr_set) {
-                DCRF_CUDA(cudaFuncSetAttribute(seg_radix_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(sizeof(int) * ((size_t)kSortWarps * kSegMaxRadix + 2 * kSegMaxRadix) +
-                                                     sizeof(uint32_t) * 2 * kSortTile)));
-                attr_set = true;
-            }
-            seg_radix_scatter_staged_kernel<<<total_tiles, kSortThreads, smem, s>>>(ki, vi, ko, vo, hist.p, si, shift,
-                                                                                   digit_bits);
-        } else {
-            seg_radix_scatter_kernel<<<total_tiles, kSortThreads, 0, s>>>(ki, vi, ko, vo, hist.p, si, shift, digit_bits);
-        }
+        seg_radix_scatter_kernel<<<total_tiles, kSortThreads, 0, s>>>(ki, ko, hist.p, si, shift, digit_bits);
         DCRF_LAUNCHED();
-        uint32_t *t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
+        uint2 *t = ki;
+        ki = ko;
+        ko = t;
     }
     return passes & 1;
 }

@@ -40,13 +40,36 @@ def _active_classes(probs_img):
 
 # a handle indexes lattice entries with int32: N * (d + 1) < 2^31 with d = 5; stay well below
 _MAX_BATCH_PIXELS = (1 << 31) // 6 // 2
+# grid.y of the per-image kernels
+_MAX_BATCH_IMAGES = 65535
 
 
-def _chunks(indices, npix):
-    """Split `indices` into consecutive runs whose total pixel count fits one handle."""
+def _bytes_per_pixel(n_labels):
+    """Device memory one pixel of a Gaussian + bilateral model needs while its handle is alive, for
+    lattices of up to 4 vertices per pixel in total (VOC: 0.8, DeepGlobe with srgb = 5: 4.1): unary, Q,
+    the two value ping-pong buffers per lattice, the entry / CSR tables and the build temporaries."""
+    lp = (int(n_labels) + 3) // 4 * 4
+    return 40 * lp + 830
+
+
+def _pixel_budget(n_labels, device=None):
+    """Pixels per handle: the int32 entry bound, or what 60 % of the free device memory holds."""
+    import ctypes as C
+
+    from . import _lib
+
+    free = C.c_int64(0)
+    _lib.check(_lib.load().dcrf_mem_info(-1 if device is None else int(device), C.byref(free), None))
+    return max(1, min(_MAX_BATCH_PIXELS, int(0.6 * free.value) // _bytes_per_pixel(n_labels)))
+
+
+def _chunks(indices, npix, max_pixels=None):
+    """Split `indices` into consecutive runs whose total pixel count fits one handle (and whose
+    image count fits a launch grid).  An image larger than the budget runs alone."""
+    budget = _MAX_BATCH_PIXELS if max_pixels is None else max_pixels
     out, cur, tot = [], [], 0
     for i in indices:
-        if cur and tot + npix[i] > _MAX_BATCH_PIXELS:
+        if cur and (tot + npix[i] > budget or len(cur) >= _MAX_BATCH_IMAGES):
             out.append(cur)
             cur, tot = [], 0
         cur.append(i)
@@ -54,6 +77,26 @@ def _chunks(indices, npix):
     if cur:
         out.append(cur)
     return out
+
+
+def _run_chunked(indices, npix, n_labels, device, fn, budget=None):
+    """fn(idx) for every memory-sized chunk of `indices`; a chunk that still runs out of device memory
+    (lattices denser than the estimate) is halved and retried."""
+    from .densecrf import trim_memory
+
+    work = _chunks(indices, npix, _pixel_budget(n_labels, device) if budget is None else budget)
+    while work:
+        idx = work.pop(0)
+        try:
+            fn(idx)
+        except MemoryError:
+            if len(idx) == 1:
+                raise
+            try:
+                trim_memory()
+            except RuntimeError:
+                pass
+            work = [idx[:len(idx) // 2], idx[len(idx) // 2:]] + work
 
 
 def _group_by(keys):
@@ -86,21 +129,24 @@ def dcrf_process(probs, images, config, device=None):
     # classes] (first maximum wins in both): only the int32 label map leaves the GPU.
     out = np.zeros((num_input_images, H, W), dtype=np.int64)
     active = [_active_classes(probs[i]) for i in range(num_input_images)]
-    groups = []
     for n_act, members in _group_by([len(a) for a in active]).items():
-        groups += [(n_act, c) for c in _chunks(members, [H * W] * num_input_images)]
-    for n_act, idx in groups:
         if n_act == 0:
             continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0 -> label 0
-        d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
-        d.setUnaryFromSoftmax([probs[i, active[i]] for i in idx])  # clip + -log on the GPU (utilities.py:431)
-        d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
-        d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=[np.uint8(images[i]) for i in idx],
-                               compat=bilat_compat)
-        labels = d.map(n_infer)
-        d.close()
-        for j, i in enumerate(idx):
-            out[i] = active[i][labels[j]]
+
+        def run(idx, n_act=n_act):
+            d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
+            try:
+                d.setUnaryFromSoftmax([probs[i, active[i]] for i in idx])  # clip + -log on the GPU (utilities.py:431)
+                d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
+                d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=[np.uint8(images[i]) for i in idx],
+                                       compat=bilat_compat)
+                labels = d.map(n_infer, dtype=np.uint8 if n_act <= 256 else np.int32)
+            finally:
+                d.close()
+            for j, i in enumerate(idx):
+                out[i] = active[i][labels[j]]
+
+        _run_chunked(members, [H * W] * num_input_images, n_act, device, run)
     return out
 
 
@@ -121,7 +167,7 @@ def _dcrf_process_device(probs, images, config):
     out = torch.zeros((B, H, W), dtype=torch.int64, device=dev)
     groups = []
     for n_act, members in _group_by([len(a) for a in active]).items():
-        groups += [(n_act, c) for c in _chunks(members, [H * W] * B)]
+        groups += [(n_act, c) for c in _chunks(members, [H * W] * B, _pixel_budget(n_act, dev.index))]
     for n_act, idx in groups:
         if n_act == 0:
             continue
@@ -167,7 +213,7 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
         dev = featmaps.device
         img8 = imgs.to(device=dev, dtype=torch.uint8).contiguous()
         res = torch.empty((B, H, W, C_), dtype=torch.float32, device=dev)
-        for idx in _chunks(range(B), [H * W] * B):
+        for idx in _chunks(range(B), [H * W] * B, _pixel_budget(num_classes, dev.index)):
             d = DenseCRFBatch([(W, H)] * len(idx), num_classes, device=dev.index)
             d.setUnaryFromLogits(featmaps[idx[0]:idx[-1] + 1].to(torch.float32).contiguous(), use_log)
             d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
@@ -179,19 +225,23 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
         return res
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     out = [None] * len(imgs)
-    for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
-        sizes = [all_sizes[i] for i in idx]
-        d = DenseCRFBatch(sizes, num_classes, device=device)
-        d.setUnaryFromLogits([np.asarray(featmaps[i], dtype=np.float32) for i in idx], use_log)
-        d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
-        d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
-                               rgbim=[np.ascontiguousarray(imgs[i], dtype=np.uint8) for i in idx],
-                               compat=crf_config["bi_compat"])
-        d.run(crf_config["iterations"])
-        Q = d.marginals_hwc(min_prob=min_prob, log=log)
-        d.close()
+
+    def run(idx):
+        d = DenseCRFBatch([all_sizes[i] for i in idx], num_classes, device=device)
+        try:
+            d.setUnaryFromLogits([np.asarray(featmaps[i], dtype=np.float32) for i in idx], use_log)
+            d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
+            d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
+                                   rgbim=[np.ascontiguousarray(imgs[i], dtype=np.uint8) for i in idx],
+                                   compat=crf_config["bi_compat"])
+            d.run(crf_config["iterations"])
+            Q = d.marginals_hwc(min_prob=min_prob, log=log)
+        finally:
+            d.close()
         for i, q in zip(idx, Q):
             out[i] = q
+
+    _run_chunked(range(len(imgs)), [w * h for w, h in all_sizes], num_classes, device, run)
     return out
 
 
@@ -242,7 +292,7 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
         img8 = imgs.to(torch.uint8).contiguous()
         sets = [labels] + list(extra_labels)
         res = [torch.empty((B, H, W), dtype=torch.int64, device=dev) for _ in sets]
-        for idx in _chunks(range(B), [H * W] * B):
+        for idx in _chunks(range(B), [H * W] * B, _pixel_budget(n_labels, dev.index)):
             lo, hi = idx[0], idx[-1] + 1
             d = DenseCRFBatch([(W, H)] * len(idx), n_labels, device=dev.index)
             d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
@@ -256,18 +306,23 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
     all_sizes = [(int(im.shape[1]), int(im.shape[0])) for im in imgs]
     label_sets = [labels] + list(extra_labels)
     outs = [[None] * len(imgs) for _ in label_sets]
-    for idx in _chunks(range(len(imgs)), [w * h for w, h in all_sizes]):
+
+    def run(idx):
         d = DenseCRFBatch([all_sizes[i] for i in idx], n_labels, device=device)
-        d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
-        # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
-        d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
-                               rgbim=[np.ascontiguousarray(np.asarray(imgs[i]).astype(np.uint8)) for i in idx],
-                               compat=cfg["bi_compat"])
-        for k, ls in enumerate(label_sets):
-            d.setUnaryFromLabels([np.asarray(ls[i]) for i in idx], gt_prob=gt_prob, zero_unsure=False)
-            for i, o in zip(idx, d.map(t)):
-                outs[k][i] = o.astype(np.int64)
-        d.close()
+        try:
+            d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
+            # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
+            d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"],
+                                   rgbim=[np.ascontiguousarray(np.asarray(imgs[i]).astype(np.uint8)) for i in idx],
+                                   compat=cfg["bi_compat"])
+            for k, ls in enumerate(label_sets):
+                d.setUnaryFromLabels([np.asarray(ls[i]) for i in idx], gt_prob=gt_prob, zero_unsure=False)
+                for i, o in zip(idx, d.map(t, dtype=np.uint8 if n_labels <= 256 else np.int32)):
+                    outs[k][i] = o.astype(np.int64)
+        finally:
+            d.close()
+
+    _run_chunked(range(len(imgs)), [w * h for w, h in all_sizes], n_labels, device, run)
     return outs[0] if not extra_labels else outs
 
 
