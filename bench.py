@@ -570,6 +570,9 @@ def run_ours(args):
         from wsss_analysis_b200.evaluation import CollectiveComm
 
         comm = CollectiveComm(rank, world, local) if world > 1 else None   # ncclComm_t made through the C ABI
+        # untimed warm-up on the first images of this rank's shard (memory pool, kernel images)
+        SW.run_sweep_device(3 * SWEEP_BATCH * world, SWEEP_LABELS, rank, world, batch=SWEEP_BATCH, device=local,
+                            all_reduce=False, verify=False)
         sr = SW.run_sweep_device(SWEEP_IMAGES, SWEEP_LABELS, rank, world, batch=SWEEP_BATCH, device=local, comm=comm)
         if comm is not None:
             comm.close()

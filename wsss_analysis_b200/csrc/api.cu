@@ -157,6 +157,34 @@ cudaMemPool_t stream_pool(cudaStream_t stream) {
     return pool;
 }
 
+// Pre-grow a stream's pool to `want` bytes in ONE contiguous block (allocate + free: the release
+// threshold keeps it).  Without slack the pool settles at a reserved size just above a handle's peak
+// and, its free space being fragmented, cudaMallocFromPoolAsync then re-maps physical memory behind
+// the larger requests -- measured (DCRF_TRACE=1, 8 ADP 1088^2 images per handle): stalls of 10-900 ms
+// in one step out of three, with the reserved size constant.  One early growth to the estimated
+// footprint of the handle replaces them.  Best effort: a failed reservation is not an error.
+static void pool_reserve(cudaStream_t stream, size_t want) {
+    static const double factor = [] {
+        const char *e = getenv("DCRF_POOL_RESERVE_FACTOR");
+        return e ? atof(e) : 1.0;
+    }();
+    want = (size_t)((double)want * factor);
+    if (want == 0) return;
+    cudaMemPool_t pool = stream_pool(stream);
+    uint64_t reserved = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) return;
+    if (reserved >= want) return;
+    want += want / 4;  // head-room: batches of slightly varying size (a sweep over mixed image sizes) grow once
+    void *p = nullptr;
+    const double t0 = trace_now();
+    if (cudaMallocFromPoolAsync(&p, want, pool, stream) != cudaSuccess) {
+        cudaGetLastError();  // not enough memory for the slack: run without it
+        return;
+    }
+    cudaFreeAsync(p, stream);
+    trace_slow("pool_reserve (one-time growth of the stream's pool)", t0, want);
+}
+
 static void trim_all_pools() {
     std::lock_guard<std::mutex> lock(g_pool_mu);
     for (auto &kv : g_pools) cudaMemPoolTrimTo(kv.second, 0);
@@ -330,6 +358,9 @@ void create_common(int B, const int *w, const int *hgt, bool has_geom, int L, in
     g.d_w = h->d_w.p;
     g.d_h = h->d_h.p;
     g.d_pix_start = h->d_pix_start.p;
+    // estimated device footprint of a Gaussian + bilateral model on this batch (lattices of up to ~4
+    // vertices per pixel in total; wsss.py sizes its batches with the same figure)
+    pool_reserve(h->stream, (size_t)g.Ntot * (size_t)(40 * std::max(h->Lp, 4) + 830));
     if (h->Lp > 0) {
         h->unary.alloc((size_t)g.Ntot * h->Lp, h->stream);
         h->Q.alloc((size_t)g.Ntot * h->Lp, h->stream);
@@ -665,6 +696,15 @@ void dcrf_destroy(dcrf_t *h) {
             cudaStreamSynchronize(h->stream);
             cudaEventDestroy(h->ev_fork);
             for (int k = 0; k < kMaxPairwise - 1; k++) cudaEventDestroy(h->ev_join[k]);
+        }
+        if (t0 != 0.0) {  // DCRF_TRACE: state of the handle's pool after everything was freed
+            uint64_t reserved = 0, used = 0, high = 0;
+            cudaMemPool_t pool = stream_pool(h->stream);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high);
+            fprintf(stderr, "[dcrf trace] pool of stream %p: reserved %.1f MB, in use %.1f MB, high-water %.1f MB\n",
+                    (void *)h->stream, reserved / 1e6, used / 1e6, high / 1e6);
         }
         h->streams.reset();  // the last holder destroys the set's streams and their pools
         trace_slow("dcrf_destroy", t0, 0);
