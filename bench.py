@@ -539,6 +539,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1
+    # (NCCL prints its version banner there when a communicator is created) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -693,7 +698,7 @@ def run_ours(args):
         "sweep": sw,
         "configs": others if others else None,
     }
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -436,3 +436,35 @@ def test_handle_outlives_its_creating_thread():
         o.addPairwiseBilateral(sxy=80, srgb=13, rgbim=img, compat=10)
         assert np.abs(box["g"].inference(5) - o.inference(5)).max() <= 1e-4   # side streams created after the thread died
         box.pop("g").close()
+
+
+def test_wrappers_take_an_arithmetic_mode():
+    """the drop-in wrappers can select the arithmetic -- per call (`arithmetic=`) or for
+    every call site at once (`wsss.ARITHMETIC`)."""
+    from wsss_analysis_b200 import densecrf as G
+    from wsss_analysis_b200 import synthetic as S
+    from wsss_analysis_b200 import wsss
+
+    cfg = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 80, "bi_srgb": 13, "bi_compat": 10, "iterations": 5}
+    H, W, C_ = 40, 52, 21
+    rng = np.random.default_rng(3)
+    feat = rng.standard_normal((H, W, C_)).astype(np.float32) * 2
+    img = S.natural_image(H, W, 3)
+    direct = {}
+    for mode in ("fma", "strict"):
+        d = G.DenseCRFBatch([(W, H)], C_)
+        d.set_arithmetic(mode)
+        d.setUnaryFromLogits([feat])
+        d.addPairwiseGaussian(sxy=3, compat=3)
+        d.addPairwiseBilateral(sxy=80, srgb=13, rgbim=[img], compat=10)
+        d.run(5)
+        direct[mode] = d.marginals_hwc()[0]
+        d.close()
+    assert not np.array_equal(direct["fma"], direct["strict"])
+    assert np.array_equal(wsss.crf_inference(img, cfg, C_, feat, arithmetic="strict"), direct["strict"])
+    assert np.array_equal(wsss.crf_inference(img, cfg, C_, feat), direct["fma"])         # auto -> fma at srgb = 13
+    wsss.ARITHMETIC = "strict"
+    try:
+        assert np.array_equal(wsss.crf_inference(img, cfg, C_, feat), direct["strict"])
+    finally:
+        wsss.ARITHMETIC = None

@@ -26,6 +26,20 @@ __all__ = ["dcrf_process", "crf_inference", "crf_inference_batch", "sec_crf_laye
 IRN_CRF_CONFIG = {"g_sxy": 3, "g_compat": 3, "bi_sxy": 50, "bi_srgb": 5, "bi_compat": 10, "iterations": 10}
 
 
+# arithmetic of the handles the wrappers create: None = the library default ("auto", or whatever the
+# DCRF_ARITHMETIC environment variable says); "fma" / "reference" / "strict" force a mode for every call
+# site at once (the drop-in wrappers had no way to select the exact arithmetic)
+ARITHMETIC = None
+
+
+def _new_batch(sizes, n_labels, device, arithmetic=None):
+    d = DenseCRFBatch(sizes, n_labels, device=device)
+    mode = ARITHMETIC if arithmetic is None else arithmetic
+    if mode is not None:
+        d.set_arithmetic(mode)
+    return d
+
+
 def _on_gpu(x):
     """torch CUDA tensor?  Such inputs stay on the GPU: unaries, images, marginals and label maps are
     handed to / returned by the library as device pointers and the result is a
@@ -107,7 +121,7 @@ def _group_by(keys):
     return groups
 
 
-def dcrf_process(probs, images, config, device=None):
+def dcrf_process(probs, images, config, device=None, arithmetic=None):
     """Drop-in for `dcrf_process(probs, images, config)` (03c_hsn/utilities.py:399-445).
 
     probs  (B, C, H, W) class probabilities; images (B, H, W, 3) any dtype (cast with np.uint8 like
@@ -118,7 +132,7 @@ def dcrf_process(probs, images, config, device=None):
     Images are grouped by their number of active classes and each group runs as one batch."""
     gauss_sxy, gauss_compat, bilat_sxy, bilat_srgb, bilat_compat, n_infer = config
     if _on_gpu(probs):
-        return _dcrf_process_device(probs, images, config)
+        return _dcrf_process_device(probs, images, config, arithmetic)
     probs = np.asarray(probs)
     num_input_images, num_classes = probs.shape[0], probs.shape[1]
     size = images.shape[1:3]
@@ -134,7 +148,7 @@ def dcrf_process(probs, images, config, device=None):
             continue  # the reference builds DenseCRF2D(w, h, 0) and leaves crf[i] = 0 -> label 0
 
         def run(idx, n_act=n_act):
-            d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=device)
+            d = _new_batch([(W, H)] * len(idx), n_act, device, arithmetic)
             try:
                 d.setUnaryFromSoftmax([probs[i, active[i]] for i in idx])  # clip + -log on the GPU (utilities.py:431)
                 d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
@@ -150,7 +164,7 @@ def dcrf_process(probs, images, config, device=None):
     return out
 
 
-def _dcrf_process_device(probs, images, config):
+def _dcrf_process_device(probs, images, config, arithmetic=None):
     """dcrf_process for CUDA tensors: probs (B, C, H, W) float64 / float32, images (B, H, W, 3) any
     dtype; returns a (B, H, W) int64 CUDA tensor.  Only the (B, C) table of active classes is read on
     the host (it decides how the images are grouped into batches)."""
@@ -172,7 +186,7 @@ def _dcrf_process_device(probs, images, config):
         if n_act == 0:
             continue
         act_t = [torch.as_tensor(active[i], device=dev) for i in idx]
-        d = DenseCRFBatch([(W, H)] * len(idx), n_act, device=dev.index)
+        d = _new_batch([(W, H)] * len(idx), n_act, dev.index, arithmetic)
         d.setUnaryFromSoftmax(torch.cat([probs[i].index_select(0, a).reshape(-1) for i, a in zip(idx, act_t)]))
         d.addPairwiseGaussian(sxy=gauss_sxy, compat=gauss_compat)
         d.addPairwiseBilateral(sxy=bilat_sxy, srgb=bilat_srgb, rgbim=img8[idx].contiguous(), compat=bilat_compat)
@@ -201,7 +215,7 @@ def _unary_from_featmap(feat, use_log=True):
 
 
 def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, device=None, min_prob=None,
-                        log=False):
+                        log=False, arithmetic=None):
     """Batched `crf_inference`: imgs list of (H_b, W_b, 3) uint8, featmaps list of (H_b, W_b, C).
     Returns a list of (H_b, W_b, C) float32 marginals (written in that layout by the GPU).
     `min_prob` / `log`: the clamp + renormalise + log epilogue of the SEC / DSRG `crf` closure."""
@@ -214,7 +228,7 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
         img8 = imgs.to(device=dev, dtype=torch.uint8).contiguous()
         res = torch.empty((B, H, W, C_), dtype=torch.float32, device=dev)
         for idx in _chunks(range(B), [H * W] * B, _pixel_budget(num_classes, dev.index)):
-            d = DenseCRFBatch([(W, H)] * len(idx), num_classes, device=dev.index)
+            d = _new_batch([(W, H)] * len(idx), num_classes, dev.index, arithmetic)
             d.setUnaryFromLogits(featmaps[idx[0]:idx[-1] + 1].to(torch.float32).contiguous(), use_log)
             d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
             d.addPairwiseBilateral(sxy=crf_config["bi_sxy"], srgb=crf_config["bi_srgb"],
@@ -227,7 +241,7 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
     out = [None] * len(imgs)
 
     def run(idx):
-        d = DenseCRFBatch([all_sizes[i] for i in idx], num_classes, device=device)
+        d = _new_batch([all_sizes[i] for i in idx], num_classes, device, arithmetic)
         try:
             d.setUnaryFromLogits([np.asarray(featmaps[i], dtype=np.float32) for i in idx], use_log)
             d.addPairwiseGaussian(sxy=crf_config["g_sxy"], compat=crf_config["g_compat"])
@@ -245,21 +259,22 @@ def crf_inference_batch(imgs, crf_config, num_classes, featmaps, use_log=True, d
     return out
 
 
-def crf_inference(img, crf_config, num_classes, featmap, use_log=True, device=None):
+def crf_inference(img, crf_config, num_classes, featmap, use_log=True, device=None, arithmetic=None):
     """Drop-in for SEC/DSRG's `crf_inference(img, crf_config, num_classes, featmap, use_log=True)`
     (call sites 03a_sec-dsrg/SEC.py:275, model.py:689-693): (H, W, 3) uint8 image + (H, W, C) feature
     map -> (H, W, C) float32 marginals."""
-    return crf_inference_batch([img], crf_config, num_classes, [featmap], use_log, device)[0]
+    return crf_inference_batch([img], crf_config, num_classes, [featmap], use_log, device, arithmetic=arithmetic)[0]
 
 
-def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, device=None):
+def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, device=None, arithmetic=None):
     """The `crf` closure run through tf.py_func in SEC.py:270-280 / DSRG.py:323-332, whole batch in
     one handle: featemap (B, h, w, C) float32, image (B, h, w, 3) float -> uint8;
     returns log of the clamped (>= min_prob), renormalised marginals, (B, h, w, C) float32.
     CUDA tensors in -> CUDA tensor out (the training hook of SURVEY.md 8f rank 2: nothing but batch
     geometry crosses PCIe)."""
     if _on_gpu(featemap):
-        return crf_inference_batch(image, crf_config, num_classes, featemap, use_log=True, min_prob=min_prob, log=True)
+        return crf_inference_batch(image, crf_config, num_classes, featemap, use_log=True, min_prob=min_prob, log=True,
+                                   arithmetic=arithmetic)
     featemap = np.asarray(featemap)
     batch_size = featemap.shape[0]
     image = np.asarray(image).astype(np.uint8)
@@ -267,7 +282,7 @@ def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, devic
     # clamp, the sum (NumPy's float32 order) and the quotient are bit-identical to the NumPy lines
     out = crf_inference_batch([image[i] for i in range(batch_size)], crf_config, num_classes,
                               [featemap[i] for i in range(batch_size)], use_log=True, device=device,
-                              min_prob=min_prob, log=True)
+                              min_prob=min_prob, log=True, arithmetic=arithmetic)
     ret = np.zeros(featemap.shape, dtype=np.float32)
     for i in range(batch_size):
         ret[i, :, :, :] = out[i]
@@ -275,7 +290,7 @@ def sec_crf_layer(featemap, image, crf_config, num_classes, min_prob=1e-4, devic
 
 
 def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_config=None, device=None,
-                              extra_labels=()):
+                              extra_labels=(), arithmetic=None):
     """Batched `crf_inference_label`: returns a list of (H_b, W_b) int label maps.
 
     `extra_labels`: further label sets for the SAME images (each a list like `labels`).  The
@@ -294,7 +309,7 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
         res = [torch.empty((B, H, W), dtype=torch.int64, device=dev) for _ in sets]
         for idx in _chunks(range(B), [H * W] * B, _pixel_budget(n_labels, dev.index)):
             lo, hi = idx[0], idx[-1] + 1
-            d = DenseCRFBatch([(W, H)] * len(idx), n_labels, device=dev.index)
+            d = _new_batch([(W, H)] * len(idx), n_labels, dev.index, arithmetic)
             d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
             d.addPairwiseBilateral(sxy=cfg["bi_sxy"], srgb=cfg["bi_srgb"], rgbim=img8[lo:hi], compat=cfg["bi_compat"])
             for k, ls in enumerate(sets):
@@ -308,7 +323,7 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
     outs = [[None] * len(imgs) for _ in label_sets]
 
     def run(idx):
-        d = DenseCRFBatch([all_sizes[i] for i in idx], n_labels, device=device)
+        d = _new_batch([all_sizes[i] for i in idx], n_labels, device, arithmetic)
         try:
             d.addPairwiseGaussian(sxy=cfg["g_sxy"], compat=cfg["g_compat"])
             # the IRN loaders hand over float32 0-255 HWC images (voc12/dataloader.py:93,102-103)
@@ -326,9 +341,10 @@ def crf_inference_label_batch(imgs, labels, n_labels=21, t=10, gt_prob=0.7, crf_
     return outs[0] if not extra_labels else outs
 
 
-def crf_inference_label(img, labels, dataset=None, t=10, n_labels=21, gt_prob=0.7, device=None):
+def crf_inference_label(img, labels, dataset=None, t=10, n_labels=21, gt_prob=0.7, device=None, arithmetic=None):
     """Drop-in for `imutils.crf_inference_label(img, labels, dataset, n_labels=...)`
     (03b_irn/step/cam_to_ir_label.py:35,47,52,67).  `dataset` is this fork's extra positional
     argument; its effect in the missing wrapper is unknown and it is ignored here."""
     del dataset
-    return crf_inference_label_batch([img], [labels], n_labels=n_labels, t=t, gt_prob=gt_prob, device=device)[0]
+    return crf_inference_label_batch([img], [labels], n_labels=n_labels, t=t, gt_prob=gt_prob, device=device,
+                                     arithmetic=arithmetic)[0]
