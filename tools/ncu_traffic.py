@@ -35,13 +35,18 @@ def main(rep, config="voc32", out=None):
         if cls is None:
             continue
         recs.append((cls, to_bytes(d[ir], units[ir]) + to_bytes(d[iw], units[iw]), int(float(d[ig].replace(",", "")))))
-    for cls in ("blur", "splat"):
-        grids = sorted({g for c, _, g in recs if c == cls})
+    # blur: the larger grid is the bilateral (d = 5) lattice; the splats are persistent (same grid for both
+    # lattices) and are told apart by the bytes they move (the bilateral one writes 5x more lattice rows)
+    grids = sorted({g for c, _, g in recs if c == "blur"})
+    for c, b, g in recs:
+        if c == "blur":
+            acc.setdefault("blur_kernel d=%d" % (5 if (len(grids) == 1 or g == grids[-1]) else 2), []).append(b)
+    sb = sorted(b for c, b, _ in recs if c == "splat")
+    if sb:
+        cut = (sb[0] + sb[-1]) / 2 if sb[-1] > 1.2 * sb[0] else 0
         for c, b, g in recs:
-            if c != cls:
-                continue
-            key = "%s_kernel d=%d" % (cls, 5 if (len(grids) == 1 or g == grids[-1]) else 2)
-            acc.setdefault(key, []).append(b)
+            if c == "splat":
+                acc.setdefault("splat_kernel d=%d" % (5 if b >= cut else 2), []).append(b)
     for c, b, g in recs:
         if c == "slice":
             acc.setdefault("slice_softmax_kernel (fused 2 terms)", []).append(b)

@@ -622,7 +622,7 @@ bool try_persistent(dcrf_handle *h, int n_iter) {
         va[k] = p.valA.p;
         vb[k] = p.valB.p;
     }
-    h->counters.alloc((size_t)n_iter * n, h->stream);
+    h->counters.alloc((size_t)2 * n_iter * n, h->stream);
     return launch_mean_field_persistent(lats, va, vb, a, h->unary.p, h->Q.p, h->geom.Ntot, h->L, h->Lp, n_iter,
                                         h->counters.p, h->stream);
 }

@@ -243,7 +243,7 @@ void launch_blur(const Lattice &lat, int axis, const float *in, float *out, int 
 void launch_slice_softmax(const SliceArgs &a, const float *unary, float *Q, int64_t Ntot, int L,
                           int Lp, cudaStream_t s);
 // `inference(n)` of a small problem as ONE cooperative launch (grid barriers between the phases); all
-// terms Potts, packed tables of the arithmetic in slice.fast.  counters: device int[n_iter * n_terms].
+// terms Potts, packed tables of the arithmetic in slice.fast.  counters: device int[2 * n_iter * n_terms].
 // Returns false when the configuration is not covered (nothing launched).
 bool launch_mean_field_persistent(const Lattice *const *lats, float *const *valA, float *const *valB,
                                   const SliceArgs &slice, const float *unary, float *Q, int64_t Ntot, int L, int Lp,

@@ -492,6 +492,95 @@ __global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
     splat_long_tail_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, part);
 }
 
+// Tail of the long rows, one WARP per row (round 2; replaces the CTA-per-row kernel above wherever the
+// stand-alone kernels run).  Warps claim long rows from a counter; per round the warp loads 32/g * g
+// consecutive entries with ONE coalesced request, lane group k sums entries [k g, (k + 1) g) of the round
+// (g gathers in flight), and the groups' partial sums are added in group order -- a fixed association, so the result is deterministic
+// (though not the sequential order of the specification).  With whole CTAs per row and a shared-memory
+// tree, lattices with MANY moderately long rows (histology: 30 % of the entries in rows of 256-1600
+// entries) spent most of the splat in this tail: cap 256 / 64 / 32 gave 369 / 615 / 782 us for the
+// bilateral splat of 16 HistoSegNet 321^2 images; with this kernel the cut can sit where the main
+// kernel's one-row-per-lane-group schedule stays balanced (see profiles/README.md).
+template <int G, bool REF>
+__device__ __forceinline__ void splat_tail_warp_body(
+    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
+    const int *__restrict__ n_long, int g_rt, int long_cap, int *__restrict__ counter) {
+    typedef typename CsrEnt<REF>::type Ent;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int g = G ? G : g_rt;
+    const int lane = threadIdx.x & 31, gpw = 32 / g;
+    const int sub = lane / g, c = lane - sub * g;
+    const bool on = sub < gpw;
+    const int per_round = gpw * g;  // entries per warp round: group k takes entries [k g, (k + 1) g) of the round
+    const int gbase = (sub * g) & 31;
+    const int n = *n_long;
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n) break;
+        const int v = long_rows[i];
+        const int s0 = csr_start[v] + long_cap, s1 = csr_start[v + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // one coalesced entry load per round (lane l: entry l of the round), pairs broadcast inside the group
+        Ent e_cur = (on && s0 + lane < s1) ? __ldg(csr_ent + s0 + lane) : zero_ent(Ent());
+        for (int s = s0; s < s1; s += per_round) {   // warp-uniform loop
+            const int sn = s + per_round;
+            const Ent e_next = (on && sn + lane < s1) ? __ldg(csr_ent + sn + lane) : zero_ent(Ent());
+            const int cnt = min(g, s1 - (s + sub * g));   // entries of my group in this round (may be <= 0)
+            float4 q[8];
+            if (G) {
+#pragma unroll
+                for (int k = 0; k < (G ? G : 1); k++) {
+                    const int px = __shfl_sync(FULL, e_cur.x, (gbase + k) & 31);
+                    q[k] = (on && k < cnt) ? __ldg(Q4 + ((unsigned)px * g + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < (G ? G : 1); k++) {
+                    const float w = __int_as_float(__shfl_sync(FULL, e_cur.y, (gbase + k) & 31));
+                    const float nrm = REF ? __shfl_sync(FULL, ent_norm(e_cur), (gbase + k) & 31) : 1.0f;
+                    splat_acc<REF>(acc, w, nrm, q[k]);   // padded slots add 0 * 0
+                }
+            } else {
+                for (int k = 0; k < g; k++) {
+                    const int px = __shfl_sync(FULL, e_cur.x, (gbase + k) & 31);
+                    const float w = __int_as_float(__shfl_sync(FULL, e_cur.y, (gbase + k) & 31));
+                    const float nrm = REF ? __shfl_sync(FULL, ent_norm(e_cur), (gbase + k) & 31) : 1.0f;
+                    const float4 qq = (on && k < cnt) ? __ldg(Q4 + ((unsigned)px * g + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    splat_acc<REF>(acc, w, nrm, qq);
+                }
+            }
+            e_cur = e_next;
+        }
+        // partial sums of the groups, added in group order
+        float4 tot;
+        tot.x = __shfl_sync(FULL, acc.x, c);
+        tot.y = __shfl_sync(FULL, acc.y, c);
+        tot.z = __shfl_sync(FULL, acc.z, c);
+        tot.w = __shfl_sync(FULL, acc.w, c);
+        for (int k = 1; k < gpw; k++) {
+            tot.x += __shfl_sync(FULL, acc.x, k * g + c);
+            tot.y += __shfl_sync(FULL, acc.y, k * g + c);
+            tot.z += __shfl_sync(FULL, acc.z, k * g + c);
+            tot.w += __shfl_sync(FULL, acc.w, k * g + c);
+        }
+        if (on && sub == 0) {
+            float4 o = val4[(unsigned)v * g + c];
+            o.x += tot.x; o.y += tot.y; o.z += tot.z; o.w += tot.w;
+            val4[(unsigned)v * g + c] = o;
+        }
+    }
+}
+
+template <int G, bool REF>
+__global__ void __launch_bounds__(kThreads) splat_tail_warp_kernel(
+    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
+    const int *__restrict__ n_long, int g_rt, int long_cap, int *__restrict__ counter) {
+    splat_tail_warp_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, counter);
+}
+
 // ---------------------------------------------------------------------------------------------
 // blur along one axis: out[v] = in[v] + 0.5 * (in[n1] + in[n2]); absent neighbour = zero row.
 // SEQ reproduces the value_size<=2 association (sum in float, 0.5* and outer add in double).
@@ -1387,7 +1476,7 @@ struct MfArgs {
     float4 *Q4;
     unsigned Ntot;
     int L, g, n_iter;
-    int *counters;  // [n_iter * n_terms] row dispensers of the splats, zeroed before the launch
+    int *counters;  // [2 * n_iter * n_terms] row dispensers of the splats and of their long-row tails, zeroed before the launch
 };
 
 template <int G, bool REF>
@@ -1395,7 +1484,6 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
     namespace cg = cooperative_groups;
     typedef typename CsrEnt<REF>::type Ent;
     cg::grid_group grid = cg::this_grid();
-    __shared__ float4 part[kThreads];
     const int nblk = gridDim.x, g = a.g, nt = a.slice.n_terms;
     const int n_slice_blocks = (int)(((int64_t)a.Ntot + kWarps * (32 / g) - 1) / (kWarps * (32 / g)));
     SliceArgs sa = a.slice;
@@ -1431,9 +1519,9 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
         if (any_long) {
             for (int k = 0; k < nt; k++) {
                 const MfTerm &t = a.term[k];
-                splat_long_tail_body<G, REF>(t.csr_start, reinterpret_cast<const Ent *>(t.csr_ent), a.Q4,
+                splat_tail_warp_body<G, REF>(t.csr_start, reinterpret_cast<const Ent *>(t.csr_ent), a.Q4,
                                              reinterpret_cast<float4 *>(t.valA), t.long_rows, t.n_long, g, t.long_cap,
-                                             part);
+                                             a.counters + (a.n_iter + it) * nt + k);
             }
             grid.sync();
         }
@@ -1509,8 +1597,16 @@ void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *n
     lat.csr_ent4.release();
     lat.ent.alloc(lat.E, s);
     lat.csr_ent.alloc(lat.E, s);
-    lat.row_counter.alloc(1, s);
-    lat.long_row_cap = kSplatLongRow;
+    lat.row_counter.alloc(2, s);
+    static const int env_cap = [] {
+        const char *e = getenv("DCRF_SPLAT_LONG_ROW");
+        return e ? atoi(e) : 0;
+    }();
+    // Where rows are long on average (histology: 50-75 entries per bilateral vertex, 30 % of the entries in
+    // rows of 256-1600) a lane group per row leaves too few, too uneven work units: cut rows at 48 entries
+    // and let whole warps sum the rest (bilateral splat of 16 HistoSegNet 321^2 images: 369 -> 208 us).
+    // Short-row lattices keep the cut at 256 (VOC: 450 us at 96-256, 468 at 48, 646 at 24).
+    lat.long_row_cap = env_cap > 0 ? env_cap : (lat.E >= 32 * lat.M ? 48 : kSplatLongRow);
     launch_find_long_rows(lat, s);
     pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
         lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, norm_post, lat.d + 1, lat.ent.p,
@@ -1524,7 +1620,7 @@ void launch_pack_ref_tables(Lattice &lat, const float *norm_pre, int long_row_ca
     lat.csr_ent.release();
     lat.ent.alloc(lat.E, s);
     lat.csr_ent4.alloc(lat.E, s);
-    lat.row_counter.alloc(1, s);
+    lat.row_counter.alloc(2, s);
     lat.long_row_cap = long_row_cap > 0 ? long_row_cap : kSplatLongRow;
     launch_find_long_rows(lat, s);
     const float alpha = 1.0f / (1.0f + powf(2.0f, (float)-lat.d));
@@ -1550,7 +1646,7 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
     if (REF) ents = reinterpret_cast<const Ent *>(lat.csr_ent4.p);
     else ents = reinterpret_cast<const Ent *>(lat.csr_ent.p);
     const int cap = lat.long_row_cap;
-    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, sizeof(int), s));
+    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, 2 * sizeof(int), s));  // [0] rows, [1] long-row tails
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     // entries per trip: long rows (Gaussian lattice, ~23 entries) amortise the loop overhead over 8
     // entries, short skewed rows (bilateral lattice, median 6) waste fewer predicated slots with 4
@@ -1567,8 +1663,8 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);   \
         splat_coop_kernel<GG, 1, MB, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4,           \
                                                                   (int)lat.M, lat.row_counter.p, cap);     \
-        splat_long_tail_kernel<GG, REF><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(          \
-            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap);                         \
+        splat_tail_warp_kernel<GG, REF><<<kNumSMs * 4, kThreads, 0, s>>>(                                  \
+            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap, lat.row_counter.p + 1);  \
     } break;
         switch (g) {
             DCRF_COOP_LAUNCH(4, 5)
@@ -1596,8 +1692,8 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
                                                                           (int)lat.M, g, lat.row_counter.p, cap);
         }
         // tail of very long rows (no-op grid when the lattice has none; the count lives on the device)
-        splat_long_tail_kernel<G, REF><<<kNumSMs * 2, kThreads, sizeof(float4) * kThreads, s>>>(
-            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap);
+        splat_tail_warp_kernel<G, REF><<<kNumSMs * 4, kThreads, 0, s>>>(
+            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap, lat.row_counter.p + 1);
     });
     DCRF_LAUNCHED();
     g_launches.fetch_add(1);
@@ -1917,7 +2013,7 @@ bool launch_mean_field_persistent(const Lattice *const *lats, float *const *valA
     a.g = g;
     a.n_iter = n_iter;
     a.counters = counters;
-    DCRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * std::max(1, n_iter * slice.n_terms), s));
+    DCRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * std::max(1, 2 * n_iter * slice.n_terms), s));
     switch (g) {
 #define DCRF_PERSIST_CASE(GG)                                        \
     case GG:                                                         \

@@ -698,7 +698,7 @@ void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, 
         rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, E, n_img, 0);
     }
     DCRF_LAUNCHED();
-    if (one.row_counter.p) out.row_counter.alloc(1, s);
+    if (one.row_counter.p) out.row_counter.alloc(2, s);
     launch_find_long_rows(out, s);
     if (norm_one && norm_out) {
         rep_f32_kernel<<<grid(n_img), kThreads, 0, s>>>(norm_one, norm_out, n_img);
