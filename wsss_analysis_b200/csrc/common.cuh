@@ -181,7 +181,7 @@ struct Lattice {
     // ent = (vertex id, bary * alpha), csr_ent4 = (pixel, weight, pre-norm[pixel] or 1, 0)
     DevBuf<int4> csr_ent4;         // [E]
     int table_mode = 0;            // kTables*: which of the packed tables are valid
-    int long_row_cap = 0;          // rows longer than this are cut (tail: splat_long_tail_kernel); INT_MAX = never
+    int long_row_cap = 0;          // rows longer than this are cut (tail: splat_tail_warp_kernel); INT_MAX = never
     DevBuf<int> row_counter;       // [1] dynamic row-chunk dispenser of the fast splat
     DevBuf<int32_t> long_rows;     // rows with more than kSplatLongRow entries (tail summed by a whole CTA)
     DevBuf<int> n_long;            // [1] their number (device side)

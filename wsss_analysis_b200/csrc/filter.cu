@@ -208,7 +208,7 @@ __device__ __forceinline__ float ent_norm(const int4 e) { return __int_as_float(
 constexpr int kSplatChunk = 32;
 // Rows longer than this (flat image regions collapse the bilateral lattice to a few vertices with
 // thousands of entries each) are cut: one lane group sums the first kSplatLongRow entries here, a
-// whole CTA per row sums the tail in splat_long_tail_kernel.  Natural images have no such row.
+// whole warp per row sums the tail in splat_tail_warp_kernel.
 constexpr int kSplatLongRow = 256;
 #ifndef DCRF_TUNE_SPLAT_REF_MINB
 #define DCRF_TUNE_SPLAT_REF_MINB 0  // 0: same __launch_bounds__ minimum as the FMA kernel of that G
@@ -281,7 +281,7 @@ __device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_
             if (need) {
                 nv = take ? row : -1;
                 ns = b0;
-                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;  // the rest of a very long row: splat_long_tail_kernel
+                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;  // the rest of a long row: splat_tail_warp_kernel
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
@@ -438,62 +438,72 @@ __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t 
     if (csr_start[v + 1] - csr_start[v] > long_cap) long_rows[atomicAdd(n_long, 1)] = (int32_t)v;
 }
 
-// val[v] += sum of the entries beyond the first long_cap of each long row v.  One CTA per row:
-// lane group k sums entries k, k + n_groups, ... in order, then the groups are combined by a fixed
-// binary tree in shared memory => deterministic (but not the sequential order of the specification).
+// Lattices whose rows are SHORT on average (fewer than 4 entries per vertex: a Gaussian lattice with
+// sxy <= 1, a bilateral lattice over a noisy image with a narrow colour bandwidth -- ADP 1088^2 with
+// sxy = 1: 2.6 entries per row, DeepGlobe 612^2 with srgb = 5: 1.5) leave the row queue of the kernels
+// above mostly idle: every trip reserves G gather slots per lane group and pays the queue's ballots and
+// shuffles for rows that end after one or two entries.  Here a lane group simply owns row v (static
+// mapping, no counter, no tail kernel) and sums its entries four per round, entry loads cooperative;
+// the same ascending order of additions, so the result is bit-identical to the queue kernels'.
+// Measured (B200): bilateral splat of 8 DeepGlobe 612^2 images 373 -> 268 us (step 19.3 -> 17.5 ms);
+// ADP-morph Gaussian 400 -> 386; at 5.8 entries per row (HistoSegNet Gaussian) a wash, at 3.4 with
+// outliers of 42 (ADP-func bilateral, caught by the 4-entry threshold's E < 4 M test only when the MEAN
+// is below 4) 500 -> 652: the queue kernel stays the default above the threshold.
 template <int G, bool REF>
-__device__ __forceinline__ void splat_long_tail_body(
-    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
-    const int *__restrict__ n_long, int g_rt, int long_cap, float4 *part /* shared [kThreads] */) {
-    const int g = G ? G : g_rt;
-    const int n_groups = kThreads / g;
-    const int k = threadIdx.x / g, c = threadIdx.x - k * g;
-    const bool on = k < n_groups;
-    const int n = *n_long;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int v = long_rows[i];
-        const int s0 = csr_start[v] + long_cap, s1 = csr_start[v + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on)
-            for (int s = s0 + k; s < s1; s += n_groups) {
-                const typename CsrEnt<REF>::type e = __ldg(csr_ent + s);
-                splat_acc<REF>(acc, __int_as_float(e.y), ent_norm(e), __ldg(Q4 + ((unsigned)e.x * g + c)));
-            }
-        if (on) part[k * g + c] = acc;
-        __syncthreads();
-        int width = 1;
-        while (width < n_groups) width <<= 1;
-        for (int half = width >> 1; half > 0; half >>= 1) {
-            if (on && k < half && k + half < n_groups) {
-                float4 a = part[k * g + c];
-                const float4 b = part[(k + half) * g + c];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                part[k * g + c] = a;
-            }
-            __syncthreads();
+__global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__restrict__ csr_start,
+                                                               const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                               const float4 *__restrict__ Q4,
+                                                               float4 *__restrict__ val4, int M, int g_rt) {
+    typedef typename CsrEnt<REF>::type Ent;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int U = 4;                                  // entries per round
+    const RowMap<G> rm(g_rt);
+    const int64_t v64 = rm.row();
+    const bool act = rm.lane_active() && v64 < M;
+    const unsigned g = rm.g, c = rm.col();
+    const unsigned v = act ? (unsigned)v64 : 0u;
+    const int gbase = (int)(threadIdx.x & 31) - (int)c;
+    int s = act ? csr_start[v] : 0;
+    const int s1 = act ? csr_start[v + 1] : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // cooperative entry loads: lane c of the group loads entries c, c + g, ... of the round (one request
+    // per group instead of U broadcast requests), pairs travel by shuffle; warp-uniform loop
+    const int per_lane = (U + (int)g - 1) / (int)g;       // 1 for g >= 4
+    while (__any_sync(FULL, s < s1)) {
+        Ent e[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int idx = s + (int)c + j * (int)g;
+            e[j] = (j < per_lane && (int)c + j * (int)g < U && idx < s1) ? __ldg(csr_ent + idx) : zero_ent(Ent());
         }
-        if (on && k == 0) {
-            float4 o = val4[(unsigned)v * g + c];
-            const float4 t = part[c];
-            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            val4[(unsigned)v * g + c] = o;
+        float4 q[U];
+        float w[U], nrm[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int src = (gbase + u % (int)g) & 31, slot = u / (int)g;
+            int px = 0, wy = 0;
+            float nn = 1.0f;
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (j == slot) {
+                    px = e[j].x;
+                    wy = e[j].y;
+                    nn = ent_norm(e[j]);
+                }
+            px = __shfl_sync(FULL, px, src);
+            w[u] = __int_as_float(__shfl_sync(FULL, wy, src));
+            nrm[u] = REF ? __shfl_sync(FULL, nn, src) : 1.0f;
+            q[u] = (s + u < s1) ? __ldg(Q4 + ((unsigned)px * g + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < U; u++) splat_acc<REF>(acc, (s + u < s1) ? w[u] : 0.f, nrm[u], q[u]);
+        s += U;
     }
+    if (act) val4[v * g + c] = acc;
 }
 
-template <int G, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_long_tail_kernel(
-    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
-    const int *__restrict__ n_long, int g_rt, int long_cap) {
-    extern __shared__ float4 part[];  // [n_groups][g]
-    splat_long_tail_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, part);
-}
-
-// Tail of the long rows, one WARP per row (round 2; replaces the CTA-per-row kernel above wherever the
-// stand-alone kernels run).  Warps claim long rows from a counter; per round the warp loads 32/g * g
+// val[v] += sum of the entries beyond the first long_cap of each long row v, one WARP per row (round 2;
+// round 1 used a whole CTA per row with a shared-memory tree).  Warps claim long rows from a counter; per round the warp loads 32/g * g
 // consecutive entries with ONE coalesced request, lane group k sums entries [k g, (k + 1) g) of the round
 // (g gathers in flight), and the groups' partial sums are added in group order -- a fixed association, so the result is deterministic
 // (though not the sequential order of the specification).  With whole CTAs per row and a shared-memory
@@ -1646,6 +1656,19 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
     if (REF) ents = reinterpret_cast<const Ent *>(lat.csr_ent4.p);
     else ents = reinterpret_cast<const Ent *>(lat.csr_ent.p);
     const int cap = lat.long_row_cap;
+    const float4 *q4s = reinterpret_cast<const float4 *>(Q);
+    float4 *v4s = reinterpret_cast<float4 *>(val);
+    static const int short_rows_below = [] {
+        const char *e = getenv("DCRF_SPLAT_SHORT_ROWS");   // mean entries per row below which the static kernel runs
+        return e ? atoi(e) : 4;
+    }();
+    if (lat.E < (int64_t)short_rows_below * lat.M) {
+        ProfScope prof(DCRF_K_SPLAT, lat.d, s);
+        const int nb = ceil_div(lat.M, rows_per_block(g));
+        DCRF_DISPATCH_G(g, { splat_short_kernel<G, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4s, v4s, (int)lat.M, g); });
+        DCRF_LAUNCHED();
+        return;
+    }
     DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, 2 * sizeof(int), s));  // [0] rows, [1] long-row tails
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     // entries per trip: long rows (Gaussian lattice, ~23 entries) amortise the loop overhead over 8
