@@ -446,9 +446,9 @@ __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t 
 // mapping, no counter, no tail kernel) and sums its entries four per round, entry loads cooperative;
 // the same ascending order of additions, so the result is bit-identical to the queue kernels'.
 // Measured (B200): bilateral splat of 8 DeepGlobe 612^2 images 373 -> 268 us (step 19.3 -> 17.5 ms);
-// ADP-morph Gaussian 400 -> 386; at 5.8 entries per row (HistoSegNet Gaussian) a wash, at 3.4 with
-// outliers of 42 (ADP-func bilateral, caught by the 4-entry threshold's E < 4 M test only when the MEAN
-// is below 4) 500 -> 652: the queue kernel stays the default above the threshold.
+// ADP-morph Gaussian 400 -> 386; at 5.8 entries per row (HistoSegNet Gaussian) a wash, at 4.2 with
+// outliers of 40+ (ADP-func bilateral) 500 -> 652: the queue kernel stays the default from 4 entries
+// per row upwards (DCRF_SPLAT_SHORT_ROWS moves the threshold).
 template <int G, bool REF>
 __global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__restrict__ csr_start,
                                                                const typename CsrEnt<REF>::type *__restrict__ csr_ent,
