@@ -290,9 +290,5 @@ void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t
 int segmented_radix_sort_pairs(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
                                const int32_t *d_key_base, int local_bits, cudaStream_t s,
                                std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile);
-// stable LSD radix sort of (key, value) pairs on the low `bits` bits of key (8 bits per pass).
-// Returns 0 when the sorted pairs ended in keys_a / vals_a, 1 when they ended in keys_b / vals_b.
-int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
-                      int64_t n, int bits, cudaStream_t s);
 
 }  // namespace dcrf

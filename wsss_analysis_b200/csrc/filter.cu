@@ -450,14 +450,14 @@ __global__ void __launch_bounds__(kThreads) find_long_rows_kernel(const int32_t 
 // outliers of 40+ (ADP-func bilateral) 500 -> 652: the queue kernel stays the default from 4 entries
 // per row upwards (DCRF_SPLAT_SHORT_ROWS moves the threshold).
 template <int G, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__restrict__ csr_start,
-                                                               const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-                                                               const float4 *__restrict__ Q4,
-                                                               float4 *__restrict__ val4, int M, int g_rt) {
+__device__ __forceinline__ void splat_short_body(const int32_t *__restrict__ csr_start,
+                                                 const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                 const float4 *__restrict__ Q4, float4 *__restrict__ val4, int M,
+                                                 int g_rt, int vblock) {
     typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int U = 4;                                  // entries per round
-    const RowMap<G> rm(g_rt);
+    const RowMap<G> rm(g_rt, vblock);
     const int64_t v64 = rm.row();
     const bool act = rm.lane_active() && v64 < M;
     const unsigned g = rm.g, c = rm.col();
@@ -500,6 +500,14 @@ __global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__
         s += U;
     }
     if (act) val4[v * g + c] = acc;
+}
+
+template <int G, bool REF>
+__global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__restrict__ csr_start,
+                                                               const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                               const float4 *__restrict__ Q4,
+                                                               float4 *__restrict__ val4, int M, int g_rt) {
+    splat_short_body<G, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, blockIdx.x);
 }
 
 // val[v] += sum of the entries beyond the first long_cap of each long row v, one WARP per row (round 2;
@@ -1477,7 +1485,7 @@ struct MfTerm {
     const int32_t *long_rows;
     const int *n_long;
     float *valA, *valB;
-    int M, d, long_cap, long_hint;
+    int M, d, long_cap, long_hint, short_rows;
 };
 struct MfArgs {
     MfTerm term[kMaxPairwise];
@@ -1516,6 +1524,12 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
             int *ctr = a.counters + it * nt + k;
             float4 *v4 = reinterpret_cast<float4 *>(t.valA);
             const Ent *ents = reinterpret_cast<const Ent *>(t.csr_ent);
+            if (t.short_rows) {   // same kernel choice as the launch-per-phase path (bit-identical results)
+                const int nb_rows = (t.M + kWarps * (32 / g) - 1) / (kWarps * (32 / g));
+                for (int vb = blockIdx.x; vb < nb_rows; vb += nblk)
+                    splat_short_body<G, REF>(t.csr_start, ents, a.Q4, v4, t.M, g, vb);
+                continue;
+            }
             if (G >= 4 && G <= 8) {
                 splat_coop_body<(G >= 4 && G <= 8) ? G : 4, 1, REF>(t.csr_start, ents, a.Q4, v4, t.M, ctr, t.long_cap);
             } else if (t.long_hint) {
@@ -1529,6 +1543,7 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
         if (any_long) {
             for (int k = 0; k < nt; k++) {
                 const MfTerm &t = a.term[k];
+                if (t.short_rows) continue;   // the static kernel summed whole rows
                 splat_tail_warp_body<G, REF>(t.csr_start, reinterpret_cast<const Ent *>(t.csr_ent), a.Q4,
                                              reinterpret_cast<float4 *>(t.valA), t.long_rows, t.n_long, g, t.long_cap,
                                              a.counters + (a.n_iter + it) * nt + k);
@@ -1647,6 +1662,15 @@ static int resident_blocks_per_sm(K kernel) {
     return n > 0 ? n : 1;
 }
 
+// mean entries per row below which the static short-row kernel runs (DCRF_SPLAT_SHORT_ROWS, default 4)
+static bool splat_uses_short_rows(const Lattice &lat) {
+    static const int short_rows_below = [] {
+        const char *e = getenv("DCRF_SPLAT_SHORT_ROWS");
+        return e ? atoi(e) : 4;
+    }();
+    return lat.E < (int64_t)short_rows_below * lat.M;
+}
+
 // REF = false: FMA tables (csr_ent); REF = true: reference-association tables (csr_ent4)
 template <bool REF>
 static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
@@ -1658,11 +1682,7 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
     const int cap = lat.long_row_cap;
     const float4 *q4s = reinterpret_cast<const float4 *>(Q);
     float4 *v4s = reinterpret_cast<float4 *>(val);
-    static const int short_rows_below = [] {
-        const char *e = getenv("DCRF_SPLAT_SHORT_ROWS");   // mean entries per row below which the static kernel runs
-        return e ? atoi(e) : 4;
-    }();
-    if (lat.E < (int64_t)short_rows_below * lat.M) {
+    if (splat_uses_short_rows(lat)) {
         ProfScope prof(DCRF_K_SPLAT, lat.d, s);
         const int nb = ceil_div(lat.M, rows_per_block(g));
         DCRF_DISPATCH_G(g, { splat_short_kernel<G, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4s, v4s, (int)lat.M, g); });
@@ -2028,6 +2048,7 @@ bool launch_mean_field_persistent(const Lattice *const *lats, float *const *valA
         t.d = lat.d;
         t.long_cap = lat.long_row_cap;
         t.long_hint = lat.E >= 16 * lat.M ? 1 : 0;
+        t.short_rows = splat_uses_short_rows(lat) ? 1 : 0;
     }
     a.unary4 = reinterpret_cast<const float4 *>(unary);
     a.Q4 = reinterpret_cast<float4 *>(Q);

@@ -125,82 +125,11 @@ void scan_rec(const int32_t *in, int32_t *out, int64_t n, bool write_total, cuda
 }
 
 // ---------------- radix sort ----------------
-constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortRounds = 16;                                   // 32-key rounds per warp
 constexpr int kSortTile = kSortThreads * kSortRounds;             // 4096 keys per block
 constexpr int kSortWarpChunk = 32 * kSortRounds;                  // 512 contiguous keys per warp
-
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys,
-                                                                  int32_t *__restrict__ hist,
-                                                                  int64_t n, int shift, int nb) {
-    __shared__ int h[kRadix];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll
-    for (int i = 0; i < kSortRounds; i++) {
-        int64_t idx = base + (int64_t)i * kSortThreads + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRadix - 1)], 1);
-    }
-    __syncthreads();
-    hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
-    const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-    const int32_t *__restrict__ hist_scanned, int64_t n, int shift, int nb) {
-    __shared__ int cnt[kSortWarps][kRadix];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = lane; i < kRadix; i += 32) cnt[warp][i] = 0;
-    __syncwarp();
-    const int64_t wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)warp * kSortWarpChunk;
-    uint32_t k[kSortRounds];
-    // phase A: per-warp digit counts over the warp's contiguous chunk
-#pragma unroll
-    for (int r = 0; r < kSortRounds; r++) {
-        int64_t idx = wbase + r * 32 + lane;
-        bool valid = idx < n;
-        k[r] = valid ? keys_in[idx] : 0u;
-        int digit = valid ? (int)((k[r] >> shift) & (kRadix - 1)) : (kRadix + lane);
-        unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[warp][digit] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    // phase B: turn counts into start positions: global digit offset of this block + earlier warps
-    {
-        int digit = threadIdx.x;
-        int run = hist_scanned[(int64_t)digit * nb + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < kSortWarps; w++) {
-            int c = cnt[w][digit];
-            cnt[w][digit] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    // phase C: stable scatter, warp chunk walked in order
-#pragma unroll
-    for (int r = 0; r < kSortRounds; r++) {
-        int64_t idx = wbase + r * 32 + lane;
-        bool valid = idx < n;
-        int digit = valid ? (int)((k[r] >> shift) & (kRadix - 1)) : (kRadix + lane);
-        unsigned peers = __match_any_sync(0xffffffffu, digit);
-        int rank = __popc(peers & ((1u << lane) - 1));
-        if (valid) {
-            int pos = cnt[warp][digit] + rank;
-            keys_out[pos] = k[r];
-            vals_out[pos] = vals_in[idx];
-        }
-        __syncwarp();
-        if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
-        __syncwarp();
-    }
-}
 
 
 // ---------------- segmented radix sort ----------------
@@ -348,29 +277,6 @@ namespace {
 
 void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
     scan_rec(in, out, n, true, s);
-}
-
-int radix_sort_pairs(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
-                     int64_t n, int bits, cudaStream_t s) {
-    if (n <= 0) return 0;
-    int passes = (bits + kRadixBits - 1) / kRadixBits;
-    if (passes < 1) passes = 1;
-    const int nb = ceil_div(n, kSortTile);
-    DevBuf<int32_t> hist;
-    hist.alloc((size_t)kRadix * nb + 1, s);
-    uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
-    for (int p = 0; p < passes; p++) {
-        const int shift = p * kRadixBits;
-        radix_hist_kernel<<<nb, kSortThreads, 0, s>>>(ki, hist.p, n, shift, nb);
-        DCRF_LAUNCHED();
-        scan_rec(hist.p, hist.p, (int64_t)kRadix * nb, false, s);
-        radix_scatter_kernel<<<nb, kSortThreads, 0, s>>>(ki, vi, ko, vo, hist.p, n, shift, nb);
-        DCRF_LAUNCHED();
-        uint32_t *t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
-    }
-    return passes & 1;
 }
 
 }  // namespace dcrf
