@@ -210,6 +210,7 @@ constexpr int kSplatChunk = 32;
 // thousands of entries each) are cut: one lane group sums the first kSplatLongRow entries here, a
 // whole warp per row sums the tail in splat_tail_warp_kernel.
 constexpr int kSplatLongRow = 256;
+constexpr int kSmallLatticeEntries = 4000000;  // below this many entries a lattice counts as "small" (see launch_pack_fast_tables)
 #ifndef DCRF_TUNE_SPLAT_REF_MINB
 #define DCRF_TUNE_SPLAT_REF_MINB 0  // 0: same __launch_bounds__ minimum as the FMA kernel of that G
 #endif
@@ -219,7 +220,8 @@ template <int G, int SB, bool REF>
 __device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_start,
                                                 const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                 const float4 *__restrict__ Q4, float4 *__restrict__ val4, int M,
-                                                int g_rt, int *__restrict__ row_counter, int long_cap) {
+                                                int g_rt, int *__restrict__ row_counter, int long_cap,
+                                                int chunk = kSplatChunk) {
     typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     const int g = G ? G : g_rt;
@@ -260,13 +262,13 @@ __device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_
                 // (batch of 32 VOC images, d = 5): static striding of rows 842 us, CTA-local chunk
                 // dealing 519 us, rows pre-sorted by length 597-943 us; this queue 456 us.
                 int base = 0;
-                if (lane == 0) base = atomicAdd(row_counter, kSplatChunk);
+                if (lane == 0) base = atomicAdd(row_counter, chunk);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= M) {
                     exhausted = true;
                 } else {
                     q_base = q_next = base;
-                    q_end = min(base + kSplatChunk, M);
+                    q_end = min(base + chunk, M);
                     bounds = csr_start[min(base + lane, M)];
                     bound_last = csr_start[q_end];
                 }
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__r
                                                               const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                               const float4 *__restrict__ Q4,
                                                               float4 *__restrict__ val4, int M, int g_rt,
-                                                              int *__restrict__ row_counter, int long_cap) {
-    splat_fast_body<G, SB, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, row_counter, long_cap);
+                                                              int *__restrict__ row_counter, int long_cap, int chunk) {
+    splat_fast_body<G, SB, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, row_counter, long_cap, chunk);
 }
 
 // Same schedule with COOPERATIVE entry loads: every warp-level load request costs the LSU a fixed
@@ -327,7 +329,8 @@ template <int G, int NB, bool REF>
 __device__ __forceinline__ void splat_coop_body(const int32_t *__restrict__ csr_start,
                                                 const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                 const float4 *__restrict__ Q4, float4 *__restrict__ val4, int M,
-                                                int *__restrict__ row_counter, int long_cap) {
+                                                int *__restrict__ row_counter, int long_cap,
+                                                int chunk = kSplatChunk) {
     typedef typename CsrEnt<REF>::type Ent;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int SB = G * NB;
@@ -366,13 +369,13 @@ __device__ __forceinline__ void splat_coop_body(const int32_t *__restrict__ csr_
         if (need_mask) {
             if (q_next >= q_end && !exhausted) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(row_counter, kSplatChunk);
+                if (lane == 0) base = atomicAdd(row_counter, chunk);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= M) {
                     exhausted = true;
                 } else {
                     q_base = q_next = base;
-                    q_end = min(base + kSplatChunk, M);
+                    q_end = min(base + chunk, M);
                     bounds = csr_start[min(base + lane, M)];
                     bound_last = csr_start[q_end];
                 }
@@ -425,8 +428,8 @@ __global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_
                                                               const typename CsrEnt<REF>::type *__restrict__ csr_ent,
                                                               const float4 *__restrict__ Q4,
                                                               float4 *__restrict__ val4, int M,
-                                                              int *__restrict__ row_counter, int long_cap) {
-    splat_coop_body<G, NB, REF>(csr_start, csr_ent, Q4, val4, M, row_counter, long_cap);
+                                                              int *__restrict__ row_counter, int long_cap, int chunk) {
+    splat_coop_body<G, NB, REF>(csr_start, csr_ent, Q4, val4, M, row_counter, long_cap, chunk);
 }
 
 // rows with more than long_cap entries (found at build time, any order: rows are independent)
@@ -1631,7 +1634,10 @@ void launch_pack_fast_tables(Lattice &lat, const float *norm_pre, const float *n
     // rows of 256-1600) a lane group per row leaves too few, too uneven work units: cut rows at 48 entries
     // and let whole warps sum the rest (bilateral splat of 16 HistoSegNet 321^2 images: 369 -> 208 us).
     // Short-row lattices keep the cut at 256 (VOC: 450 us at 96-256, 468 at 48, 646 at 24).
-    lat.long_row_cap = env_cap > 0 ? env_cap : (lat.E >= 32 * lat.M ? 48 : kSplatLongRow);
+    // Small lattices (a single image): a 256-entry row is a chain of 43 dependent trips of one lane group
+    // (~40 us) that nothing hides -- cut at 48 there as well (one VOC image, bilateral splat: 48 -> ? us).
+    const bool small = lat.E < (int64_t)kSmallLatticeEntries;
+    lat.long_row_cap = env_cap > 0 ? env_cap : ((lat.E >= 32 * lat.M || small) ? 48 : kSplatLongRow);
     launch_find_long_rows(lat, s);
     pack_fast_tables_kernel<<<ceil_div(lat.E, kThreads), kThreads, 0, s>>>(
         lat.offset.p, lat.bary.p, lat.csr_pix.p, lat.csr_w.p, norm_pre, norm_post, lat.d + 1, lat.ent.p,
@@ -1671,6 +1677,16 @@ static bool splat_uses_short_rows(const Lattice &lat) {
     return lat.E < (int64_t)short_rows_below * lat.M;
 }
 
+// Rows a warp claims from the queue per atomic.  Large lattices: 32 (one atomic per 32 rows, ~6 rows per
+// lane group).  Small ones (one VOC image: 126 k rows for 5920 resident warps; its Gaussian lattice:
+// 24 k) would leave most warps without a chunk and make the launch as long as one warp's ~6 rows per
+// lane group in sequence: there a chunk is ~ half a warp's fair share, at least one row per lane group.
+static int splat_chunk(int64_t M, int g, int nb) {
+    const int64_t warps = (int64_t)nb * kWarps;
+    const int64_t fair = M / (2 * std::max<int64_t>(warps, 1));
+    return (int)std::max<int64_t>(32 / g, std::min<int64_t>(kSplatChunk, fair));
+}
+
 // REF = false: FMA tables (csr_ent); REF = true: reference-association tables (csr_ent4)
 template <bool REF>
 static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {
@@ -1704,8 +1720,8 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         constexpr int MB = (REF && kSplatRefMinBlocks) ? kSplatRefMinBlocks : MINB;                         \
         static const int per_sm = resident_blocks_per_sm(splat_coop_kernel<GG, 1, MB, REF>);                \
         const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);   \
-        splat_coop_kernel<GG, 1, MB, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4,           \
-                                                                  (int)lat.M, lat.row_counter.p, cap);     \
+        splat_coop_kernel<GG, 1, MB, REF><<<nb, kThreads, 0, s>>>(                                         \
+            lat.csr_start.p, ents, q4, v4, (int)lat.M, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb)); \
         splat_tail_warp_kernel<GG, REF><<<kNumSMs * 4, kThreads, 0, s>>>(                                  \
             lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap, lat.row_counter.p + 1);  \
     } break;
@@ -1727,12 +1743,12 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
             static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, 8, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
             splat_fast_kernel<G, 8, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4, (int)lat.M, g,
-                                                                lat.row_counter.p, cap);
+                                                                lat.row_counter.p, cap, splat_chunk(lat.M, g, nb));
         } else {
             static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, kSplatBatch, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
-            splat_fast_kernel<G, kSplatBatch, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4,
-                                                                          (int)lat.M, g, lat.row_counter.p, cap);
+            splat_fast_kernel<G, kSplatBatch, REF><<<nb, kThreads, 0, s>>>(
+                lat.csr_start.p, ents, q4, v4, (int)lat.M, g, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb));
         }
         // tail of very long rows (no-op grid when the lattice has none; the count lives on the device)
         splat_tail_warp_kernel<G, REF><<<kNumSMs * 4, kThreads, 0, s>>>(
