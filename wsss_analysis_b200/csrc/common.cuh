@@ -287,6 +287,12 @@ void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t
 // Stable LSD radix sort of interleaved (key, value) pairs inside consecutive segments, by
 // (key - key_base[segment]) on `local_bits` bits.  Returns 0 when the sorted pairs ended in pairs_a, 1
 // when they ended in pairs_b.  h_seg / h_tile: caller-owned staging of two small uploads.
+// one stable pass on the high bits + a counting sort per bucket that writes the CSR arrays; false = not
+// applicable (vertex ids of an image need more than 23 bits): use segmented_radix_sort_pairs
+bool bucket_sort_to_csr(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
+                        const int32_t *d_key_base, int local_bits, const float *bary, int d1, int64_t E, int64_t M,
+                        int32_t *csr_start, int32_t *csr_pix, float *csr_w, int prof_tag, cudaStream_t s,
+                        std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile);
 int segmented_radix_sort_pairs(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
                                const int32_t *d_key_base, int local_bits, cudaStream_t s,
                                std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile);

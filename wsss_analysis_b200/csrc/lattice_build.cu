@@ -5,8 +5,10 @@
 // sequential `Permutohedral::init` [EXT] specified in SURVEY.md Appendix A.3:
 //   K1  point kernel : features -> elevate -> nearest remainder-0 point -> rank -> barycentric
 //   K2  hash insert  : open-addressing table of lattice keys, slot value = min entry index
-//   K3  numbering    : first-occurrence flags + exclusive scan  => the reference's vertex ids
+//   K3  numbering    : per-pixel first-occurrence masks + exclusive scan of their counts
+//                      => the reference's vertex ids
 //   K4  assign       : offsets, vertex keys; compact (L2-resident) table of vertex ids
+//   (K2-K4 skip "duplicate" pixels -- same simplex as their left neighbour -- see run_leader)
 //   K5  neighbours   : +-1 neighbours along each of the d+1 axes by table lookup
 //   K6  CSR          : stable radix sort of entries by vertex id => rows of the transposed
 //                      incidence matrix in ascending entry order (deterministic splat)
@@ -185,15 +187,22 @@ __global__ void __launch_bounds__(kThreads) lattice_point_kernel(
     for (int i = 0; i <= D; i++) {
         float v = __fmul_rn(__fsub_rn(e[i], rem0[i]), down_factor);
         int idx = D - rank[i];
+        // (selects, not branches: an `if (k == idx)` form is turned into a dynamically indexed local array)
 #pragma unroll
         for (int k = 0; k <= D + 1; k++) {
-            if (k == idx) bc[k] = __fadd_rn(bc[k], v);
-            if (k == idx + 1) bc[k] = __fsub_rn(bc[k], v);
+            const float up = __fadd_rn(bc[k], v), dn = __fsub_rn(bc[k], v);
+            bc[k] = (k == idx) ? up : ((k == idx + 1) ? dn : bc[k]);
         }
     }
     bc[0] = (float)((double)bc[0] + (1.0 + (double)bc[D + 1]));
+    if ((D + 1) % 2 == 0) {  // 8-byte aligned run of d+1 floats: half the store instructions
+        float2 *bo = reinterpret_cast<float2 *>(bary_out + gp * (D + 1));
 #pragma unroll
-    for (int r = 0; r <= D; r++) bary_out[gp * (D + 1) + r] = bc[r];
+        for (int r = 0; r + 1 <= D; r += 2) bo[r / 2] = make_float2(bc[r], bc[r + 1]);
+    } else {
+#pragma unroll
+        for (int r = 0; r <= D; r++) bary_out[gp * (D + 1) + r] = bc[r];
+    }
     // pixel record: first D coordinates of rem0 as int16, first D ranks as nibbles
     short rm[8];
     uint32_t rp = 0;
@@ -211,21 +220,52 @@ __global__ void __launch_bounds__(kThreads) lattice_point_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: hash insert.  One thread per pixel, d+1 inserts.  table[] holds entry indices (-1 = empty);
-// a slot's key never changes once claimed, only its representative shrinks (atomicMin).
+// Run leaders.  Neighbouring pixels of a natural image very often fall into the SAME simplex with the
+// same remainder-0 point: their pixel records (rem0, rank) are equal, hence all d+1 lattice keys are.
+// Such a pixel ("duplicate") can never hold the first occurrence of a key -- its left neighbour has the
+// same keys at smaller entry indices -- so K2-K4 let only the first pixel of a run inside a warp (the
+// "leader") touch the hash table and the numbering arrays; the duplicates copy the leader's vertex ids
+// with a shuffle.  K2, K3 and K4 use the same pixel <-> lane mapping, so each recomputes the same flags.
+// ---------------------------------------------------------------------------------------------
+struct RunLeader {
+    bool leader;   // this lane does the look-ups itself
+    int src;       // lane to copy from (== own lane for a leader)
+};
+__device__ __forceinline__ RunLeader run_leader(bool valid, bool first_of_image, const int4 rem,
+                                                const uint32_t rp) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int px = __shfl_up_sync(FULL, rem.x, 1), py = __shfl_up_sync(FULL, rem.y, 1);
+    const int pz = __shfl_up_sync(FULL, rem.z, 1), pw = __shfl_up_sync(FULL, rem.w, 1);
+    const uint32_t pr = __shfl_up_sync(FULL, rp, 1);
+    const bool dup = valid && lane > 0 && !first_of_image && px == rem.x && py == rem.y && pz == rem.z &&
+                     pw == rem.w && pr == rp;
+    const unsigned leaders = __ballot_sync(FULL, !dup);
+    RunLeader r;
+    r.leader = valid && !dup;
+    r.src = 31 - __clz(leaders & (FULL >> (31 - lane)));  // lane 0 is always a leader
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: hash insert.  One thread per pixel, d+1 inserts by the run leaders.  table[] holds entry indices
+// (-1 = empty); a slot's key never changes once claimed, only its representative shrinks (atomicMin).
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
     GeomDev g, int64_t Ntot, const int64_t *__restrict__ tab_start, const int *__restrict__ tab_mask,
     const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank, int32_t *table,
     int32_t *__restrict__ slot_of) {
-    const int64_t gp = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (gp >= Ntot) return;
+    const int64_t gp0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = gp0 < Ntot;
+    const int64_t gp = valid ? gp0 : Ntot - 1;
     const int b = find_image(g.pix_start, g.B, gp);
     int32_t *tab = table + tab_start[b];
     const uint32_t mask = (uint32_t)tab_mask[b];
     const int4 rem = rec_rem[gp];
     const uint32_t rp = rec_rank[gp];
+    const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rem, rp);
+    if (!rl.leader) return;  // no warp-level operation below
 #pragma unroll 1
     for (int r = 0; r <= D; r++) {
         short key[8];
@@ -250,40 +290,81 @@ __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
             }
             h = (h + 1) & mask;
         }
-        slot_of[e] = (int32_t)h;
+        slot_of[e] = (int32_t)h;  // leaders' entries only; the duplicates' slots are never read
     }
 }
 
-// K3: flag[e] = 1 iff entry e is the first occurrence of its key
+// K3: per pixel, which of its d+1 entries are the first occurrence of their key (bit r of mask8) and how
+// many (cnt, scanned into the vertex ids); the slot of every leader entry is replaced by the table's
+// representative entry, so that K4 does not probe the (DRAM-sized) table again.
 template <int D>
-__global__ void __launch_bounds__(kThreads) first_flag_kernel(
-    GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
-    const int32_t *__restrict__ slot_of, int32_t *__restrict__ flag) {
-    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= E) return;
-    const int b = find_image(g.pix_start, g.B, e / (D + 1));
-    flag[e] = (table[tab_start[b] + slot_of[e]] == (int32_t)e) ? 1 : 0;
+__global__ void __launch_bounds__(kThreads) first_mask_kernel(
+    GeomDev g, int64_t Ntot, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
+    const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank, int32_t *__restrict__ slot_rep,
+    int32_t *__restrict__ cnt, uint8_t *__restrict__ mask8) {
+    const int64_t gp0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = gp0 < Ntot;
+    const int64_t gp = valid ? gp0 : Ntot - 1;
+    const int b = find_image(g.pix_start, g.B, gp);
+    const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rec_rem[gp], rec_rank[gp]);
+    if (!valid) return;
+    unsigned m = 0;
+    if (rl.leader) {
+        const int32_t *tab = table + tab_start[b];
+        int32_t rep[D + 1];
+#pragma unroll
+        for (int r = 0; r <= D; r++) rep[r] = tab[slot_rep[gp * (D + 1) + r]];
+#pragma unroll
+        for (int r = 0; r <= D; r++) {
+            const int32_t e = (int32_t)(gp * (D + 1) + r);
+            slot_rep[e] = rep[r];
+            if (rep[r] == e) m |= 1u << r;
+        }
+    }
+    cnt[gp] = __popc(m);
+    mask8[gp] = (uint8_t)m;
 }
 
-// K4a: offsets for all entries; first occurrences also publish their vertex key
+// K4: vertex id of every entry = (first occurrences in the pixels before the representative's pixel)
+// + (first occurrences among the lower remainders of that pixel); offsets, (vertex, entry) sort pairs,
+// and the keys of the vertices (published by their first occurrences).
 template <int D>
 __global__ void __launch_bounds__(kThreads) assign_kernel(
-    GeomDev g, int64_t E, const int64_t *__restrict__ tab_start, const int32_t *__restrict__ table,
-    const int32_t *__restrict__ slot_of, const int32_t *__restrict__ scanned,
-    const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
+    GeomDev g, int64_t Ntot, const int32_t *__restrict__ slot_rep, const int32_t *__restrict__ pscan,
+    const uint8_t *__restrict__ mask8, const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
     int32_t *__restrict__ offset, int4 *__restrict__ vkeys, uint2 *__restrict__ sort_pairs) {
-    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (e >= E) return;
-    const int64_t gp = e / (D + 1);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int64_t gp0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = gp0 < Ntot;
+    const int64_t gp = valid ? gp0 : Ntot - 1;
     const int b = find_image(g.pix_start, g.B, gp);
-    const int32_t rep = table[tab_start[b] + slot_of[e]];
-    const int32_t id = scanned[rep];
-    offset[e] = id;
-    sort_pairs[e] = make_uint2((uint32_t)id, (uint32_t)e);  // (vertex, entry) pairs for the CSR sort (K6)
-    if (rep == (int32_t)e) {
-        short key[8];
-        entry_key<D>(rec_rem[gp], rec_rank[gp], (int)(e - gp * (D + 1)), key);
-        vkeys[id] = pack_key(key);
+    const int4 rem = rec_rem[gp];
+    const uint32_t rp = rec_rank[gp];
+    const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rem, rp);
+    const unsigned mine = rl.leader ? mask8[gp] : 0u;
+    int32_t rep[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) rep[r] = rl.leader ? slot_rep[gp * (D + 1) + r] : 0;
+    int32_t id[D + 1];
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        const int32_t pp = rep[r] / (D + 1);
+        const int rr = rep[r] - pp * (D + 1);
+        id[r] = rl.leader ? pscan[pp] + __popc((unsigned)mask8[pp] & ((1u << rr) - 1u)) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r <= D; r++) {
+        const int32_t v = __shfl_sync(FULL, id[r], rl.src);
+        if (valid) {
+            const int64_t e = gp * (D + 1) + r;
+            offset[e] = v;
+            sort_pairs[e] = make_uint2((uint32_t)v, (uint32_t)e);  // (vertex, entry) pairs for the CSR sort (K6)
+            if ((mine >> r) & 1u) {
+                short key[8];
+                entry_key<D>(rem, rp, r, key);
+                vkeys[v] = pack_key(key);
+            }
+        }
     }
 }
 
@@ -327,10 +408,11 @@ __global__ void __launch_bounds__(kThreads) neighbour_wide_kernel(
     int64_t M, int B, const int32_t *__restrict__ vert_start, const int64_t *__restrict__ tab_start,
     const int *__restrict__ tab_mask, const int4 *__restrict__ table, const int4 *__restrict__ vkeys,
     int2 *__restrict__ neigh) {
-    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (t >= M * (D + 1)) return;
-    const int j = (int)(t / M);
-    const int64_t v = t - (int64_t)j * M;
+    // D+1 consecutive CTAs look up the D+1 axes of the same 256 vertices: an image's (few MB) table is
+    // probed for all axes while it is L2 resident (an axis-major grid streams every table D+1 times)
+    const int j = (int)(blockIdx.x % (D + 1));
+    const int64_t v = (int64_t)(blockIdx.x / (D + 1)) * kThreads + threadIdx.x;
+    if (v >= M) return;
     const int b = find_image(vert_start, B, v);
     const int4 *tab = table + tab_start[b];
     const uint32_t mask = (uint32_t)tab_mask[b];
@@ -356,11 +438,11 @@ __global__ void __launch_bounds__(kThreads) neighbour_wide_kernel(
     if (found >= 0) nflat[2 * (int64_t)found + 1] = (int)v;
 }
 
-// vert_start[b] = number of first occurrences before image b's first entry
-__global__ void vert_start_kernel(const int *__restrict__ pix_start, int B, int d1,
-                                  const int32_t *__restrict__ scanned, int32_t *__restrict__ vert_start) {
+// vert_start[b] = number of first occurrences before image b's first pixel
+__global__ void vert_start_kernel(const int *__restrict__ pix_start, int B,
+                                  const int32_t *__restrict__ pscan, int32_t *__restrict__ vert_start) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b <= B) vert_start[b] = scanned[(int64_t)pix_start[b] * d1];
+    if (b <= B) vert_start[b] = pscan[pix_start[b]];
 }
 
 // K5: neighbours.  One thread per (axis j, vertex v); table now holds vertex ids.  Only the first
@@ -478,17 +560,20 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
 
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_NUMBER, D, s));
-    DevBuf<int32_t> scanned;
-    scanned.alloc(E + 1, s);
+    DevBuf<int32_t> pscan;   // per pixel: count of first occurrences, scanned in place
+    DevBuf<uint8_t> mask8;   // per pixel: which remainders are first occurrences
+    pscan.alloc(Ntot + 1, s);
+    mask8.alloc(Ntot, s);
     const int nbe = ceil_div(E, kThreads);
-    first_flag_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p);
+    first_mask_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, d_tab_start.p, table.p, rec_rem.p, rec_rank.p,
+                                                 slot_of.p, pscan.p, mask8.p);
     DCRF_LAUNCHED();
-    exclusive_scan_i32(scanned.p, scanned.p, E, s);
+    exclusive_scan_i32(pscan.p, pscan.p, Ntot, s);
 
     // vertex counts: total + per image (host needs them to size everything else)
     DevBuf<int32_t> d_vert_start;
     d_vert_start.alloc(B + 1, s);
-    vert_start_kernel<<<ceil_div(B + 1, 128), 128, 0, s>>>(g.d_pix_start, B, d1, scanned.p, d_vert_start.p);
+    vert_start_kernel<<<ceil_div(B + 1, 128), 128, 0, s>>>(g.d_pix_start, B, pscan.p, d_vert_start.p);
     DCRF_LAUNCHED();
     std::vector<int32_t> h_vs(B + 1);
     DCRF_CUDA(copy_d2h(h_vs.data(), d_vert_start.p, sizeof(int32_t) * (B + 1), s));
@@ -502,8 +587,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     int4 *vkeys4 = reinterpret_cast<int4 *>(out.vkeys.p);
     DevBuf<uint2> pa, pb;  // interleaved (vertex, entry) pairs: one 8-byte scatter per pair and pass
     pa.alloc(E, s);
-    assign_kernel<D><<<nbe, kThreads, 0, s>>>(gd, E, d_tab_start.p, table.p, slot_of.p, scanned.p,
-                                             rec_rem.p, rec_rank.p, out.offset.p, vkeys4, pa.p);
+    assign_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, slot_of.p, pscan.p, mask8.p, rec_rem.p, rec_rank.p,
+                                             out.offset.p, vkeys4, pa.p);
     DCRF_LAUNCHED();
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_NEIGH, D, s));
@@ -536,7 +621,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
         compact_insert_wide_kernel<<<ceil_div(M, kThreads), kThreads, 0, s>>>(M, B, d_vert_start.p, d_tab2_start.p,
                                                                              d_tab2_mask.p, vkeys4, table2.p);
         DCRF_LAUNCHED();
-        neighbour_wide_kernel<D><<<ceil_div(M * d1, kThreads), kThreads, 0, s>>>(
+        neighbour_wide_kernel<D><<<ceil_div(M, kThreads) * d1, kThreads, 0, s>>>(
             M, B, d_vert_start.p, d_tab2_start.p, d_tab2_mask.p, table2.p, vkeys4, out.neigh.p);
         DCRF_LAUNCHED();
     } else {
@@ -562,13 +647,18 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     for (int b = 0; b < B; b++) max_mb = std::max<int64_t>(max_mb, out.vert_start[b + 1] - out.vert_start[b]);
     int bits = 1;
     while (((int64_t)1 << bits) < max_mb) bits++;
+    out.csr_start.alloc(M + 1, s);
+    out.csr_pix.alloc(E, s);
+    out.csr_w.alloc(E, s);
+    prof.reset();
+    if (bucket_sort_to_csr(pa.p, pb.p, ent_start, d_vert_start.p, bits, out.bary.p, d1, E, M, out.csr_start.p,
+                           out.csr_pix.p, out.csr_w.p, D, s, out.h_seg, out.h_tile))
+        return;
+    prof.reset(new ProfScope(DCRF_K_BUILD_SORT, D, s));
     const int in_b = segmented_radix_sort_pairs(pa.p, pb.p, ent_start, d_vert_start.p, bits, s, out.h_seg, out.h_tile);
     const uint2 *sorted = in_b ? pb.p : pa.p;
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_CSR, D, s));
-    out.csr_start.alloc(M + 1, s);
-    out.csr_pix.alloc(E, s);
-    out.csr_w.alloc(E, s);
     csr_finalize_kernel<<<nbe, kThreads, 0, s>>>(sorted, out.bary.p, d1, E, M, out.csr_start.p, out.csr_pix.p,
                                                 out.csr_w.p);
     DCRF_LAUNCHED();

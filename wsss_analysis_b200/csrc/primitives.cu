@@ -273,7 +273,194 @@ int segmented_radix_sort_pairs(uint2 *pairs_a, uint2 *pairs_b, const std::vector
 
 namespace {
 
+// ---------------- bucket sort straight into the CSR rows ----------------
+// The splat's rows are the entries sorted by (image, vertex id), stable in the entry index.  Instead of
+// two or three LSD passes plus a finalising pass, ONE stable radix pass on the HIGH bits of the local
+// vertex id groups the pairs into buckets of 2^lo_bits consecutive vertices (a few thousand entries);
+// a CTA per bucket then counting-sorts its bucket on the low bits and writes the CSR arrays directly:
+// row starts from the scanned counts, (pixel, weight) of every entry at its final position.  The second
+// pass reads a contiguous bucket and writes inside the bucket's own output range -- no global scatter,
+// no second histogram / scan, no separate finalising kernel.
+// Stability of the in-bucket placement: warp w of the CTA owns the w-th contiguous slice of the bucket
+// and a private set of per-vertex cursors; the cursors of (vertex, warp) start where the entries of
+// that vertex in the slices before w end, so every warp places its slice in order on its own, rank
+// among equal vertices inside a 32-entry round from __match_any_sync in lane order.  No block barrier
+// inside the placement loop.  Shared memory: warps * 2^lo_bits cursors (<= 64 KB: 8 warps up to 11 low
+// bits, 4 at 12, 2 at 13).
+constexpr int kBucketMaxLoBits = 13;
+constexpr int kBucketMaxThreads = 256;
+constexpr int kBucketSmemInts = 16384;  // 64 KB
+
+__global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
+    const uint2 *__restrict__ pairs, const int32_t *__restrict__ hist_scanned, SegInfo si, int hi_bits, int lo_bits,
+    const float *__restrict__ bary, int d1, int32_t E, int32_t M, int32_t *__restrict__ csr_start,
+    int32_t *__restrict__ csr_pix, float *__restrict__ csr_w) {
+    extern __shared__ int cursor[];  // [warps][1 << lo_bits]: counts, then running output positions
+    __shared__ int warp_sums[kBucketMaxThreads / 32];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    if (blockIdx.x == 0 && tid == 0) csr_start[M] = E;
+    const int radix = 1 << hi_bits;
+    const int seg = blockIdx.x >> hi_bits, digit = blockIdx.x & (radix - 1);
+    const int kb = si.key_base[seg];
+    const int Mb = si.key_base[seg + 1] - kb;
+    const int v0 = digit << lo_bits;  // first local vertex of the bucket
+    if (v0 >= Mb) return;
+    const int nv = min(1 << lo_bits, Mb - v0);
+    int start, end;
+    if (hi_bits > 0) {
+        const int tiles = si.tile_base[seg + 1] - si.tile_base[seg];
+        const int32_t *hs = hist_scanned + (int64_t)radix * si.tile_base[seg];
+        start = hs[(int64_t)digit * tiles];
+        end = digit + 1 < radix ? hs[(int64_t)(digit + 1) * tiles] : si.seg_start[seg + 1];
+    } else {
+        start = si.seg_start[seg];
+        end = si.seg_start[seg + 1];
+    }
+    const uint32_t vbase = (uint32_t)(kb + v0);
+    const int stride = 1 << lo_bits;
+    for (int j = tid; j < nwarps * stride; j += nthreads) cursor[j] = 0;
+    __syncthreads();
+    // slice of this warp: whole 32-entry rounds, the last warp takes the remainder
+    const int n = end - start;
+    const int rounds_per_warp = (n / 32 + nwarps - 1) / nwarps;
+    const int s0 = min(n, warp * rounds_per_warp * 32);
+    const int s1 = (warp == nwarps - 1) ? n : min(n, s0 + rounds_per_warp * 32);
+    int *mine = cursor + warp * stride;
+    // counts of the slice (4 loads in flight per lane)
+    {
+        int i = start + s0 + lane;
+        const int iend = start + s1;
+        for (; i + 96 < iend; i += 128) {
+            const uint32_t k0 = pairs[i].x, k1 = pairs[i + 32].x, k2 = pairs[i + 64].x, k3 = pairs[i + 96].x;
+            atomicAdd(&mine[k0 - vbase], 1);
+            atomicAdd(&mine[k1 - vbase], 1);
+            atomicAdd(&mine[k2 - vbase], 1);
+            atomicAdd(&mine[k3 - vbase], 1);
+        }
+        for (; i < iend; i += 32) atomicAdd(&mine[pairs[i].x - vbase], 1);
+    }
+    __syncthreads();
+    // row starts: scan over the vertices of (sum over the warps); cursors: (vertex, warp) in that order
+    const int per = (nv + nthreads - 1) / nthreads;
+    const int j0 = min(tid * per, nv), j1 = min(j0 + per, nv);
+    int sum = 0;
+    for (int j = j0; j < j1; j++)
+        for (int w = 0; w < nwarps; w++) sum += cursor[w * stride + j];
+    const int inc = warp_inclusive_scan(sum);
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int ws = lane < nwarps ? warp_sums[lane] : 0;
+        const int winc = warp_inclusive_scan(ws);
+        if (lane < nwarps) warp_sums[lane] = winc - ws;
+    }
+    __syncthreads();
+    int run = start + warp_sums[warp] + inc - sum;
+    for (int j = j0; j < j1; j++) {
+        csr_start[vbase + j] = run;
+        for (int w = 0; w < nwarps; w++) {
+            const int c = cursor[w * stride + j];
+            cursor[w * stride + j] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // stable placement of the slice in 32-entry rounds, R rounds per trip.  The placement itself is a short
+    // chain through shared memory; what has to be hidden is the memory latency of the pair loads and of
+    // the dependent weight gathers: pairs are requested two trips ahead, weights one trip ahead.
+    constexpr int R = 4;
+    const int ibeg = start + s0, iend = start + s1;
+    uint2 eA[R], eB[R], eC[R];
+    float wA[R], wB[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int ia = ibeg + r * 32 + lane, ib = ia + R * 32;
+        eA[r] = ia < iend ? pairs[ia] : make_uint2(0u, 0u);
+        eB[r] = ib < iend ? pairs[ib] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) wA[r] = (ibeg + r * 32 + lane < iend) ? bary[eA[r].y] : 0.f;
+    for (int base = ibeg; base < iend; base += R * 32) {  // warp-uniform loop
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int ib = base + (R + r) * 32 + lane, ic = ib + R * 32;
+            wB[r] = ib < iend ? bary[eB[r].y] : 0.f;
+            eC[r] = ic < iend ? pairs[ic] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const bool valid = base + r * 32 + lane < iend;
+            const int key = valid ? (int)(eA[r].x - vbase) : -1 - lane;
+            const unsigned peers = __match_any_sync(FULL, key);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            int pos = 0;
+            if (valid) pos = mine[key] + rank;
+            __syncwarp();
+            if (valid && rank == 0) mine[key] += __popc(peers);
+            __syncwarp();
+            if (valid) {
+                csr_pix[pos] = (int32_t)(eA[r].y / (uint32_t)d1);
+                csr_w[pos] = wA[r];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            eA[r] = eB[r];
+            wA[r] = wB[r];
+            eB[r] = eC[r];
+        }
+    }
+}
+
 }  // namespace
+
+bool bucket_sort_to_csr(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_t> &seg_start,
+                        const int32_t *d_key_base, int local_bits, const float *bary, int d1, int64_t E, int64_t M,
+                        int32_t *csr_start, int32_t *csr_pix, float *csr_w, int prof_tag, cudaStream_t s,
+                        std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile) {
+    const int S = (int)seg_start.size() - 1;
+    if (S <= 0 || E <= 0) return false;
+    int hi_bits = std::min(kSegMaxDigitBits, std::max(0, local_bits - 8));
+    const int lo_bits = std::max(1, local_bits - hi_bits);
+    if (lo_bits > kBucketMaxLoBits || ((int64_t)S << hi_bits) > (int64_t)2000000000) return false;  // LSD passes instead
+    h_seg.assign(S + 1, 0);  // staging of asynchronous uploads: owned by the caller, outlives them
+    h_tile.assign(S + 1, 0);
+    for (int i = 0; i <= S; i++) h_seg[i] = (int32_t)seg_start[i];
+    for (int i = 0; i < S; i++) h_tile[i + 1] = h_tile[i] + ceil_div(seg_start[i + 1] - seg_start[i], kSortTile);
+    const int total_tiles = h_tile[S];
+    DevBuf<int32_t> d_seg, d_tile, hist;
+    d_seg.alloc(S + 1, s);
+    d_tile.alloc(S + 1, s);
+    DCRF_CUDA(copy_h2d(d_seg.p, h_seg.data(), sizeof(int32_t) * (S + 1), s));
+    DCRF_CUDA(copy_h2d(d_tile.p, h_tile.data(), sizeof(int32_t) * (S + 1), s));
+    SegInfo si{d_seg.p, d_key_base, d_tile.p, S};
+    const uint2 *grouped = pairs_a;
+    {
+        ProfScope prof(DCRF_K_BUILD_SORT, prof_tag, s);
+        if (hi_bits > 0) {
+            const int radix = 1 << hi_bits;
+            hist.alloc((size_t)radix * total_tiles + 1, s);
+            seg_radix_hist_kernel<<<total_tiles, kSortThreads, 0, s>>>(pairs_a, hist.p, si, lo_bits, hi_bits);
+            DCRF_LAUNCHED();
+            scan_rec(hist.p, hist.p, (int64_t)radix * total_tiles, false, s);
+            seg_radix_scatter_kernel<<<total_tiles, kSortThreads, 0, s>>>(pairs_a, pairs_b, hist.p, si, lo_bits, hi_bits);
+            DCRF_LAUNCHED();
+            grouped = pairs_b;
+        }
+    }
+    ProfScope prof(DCRF_K_BUILD_CSR, prof_tag, s);
+    const int warps = std::min(kBucketMaxThreads / 32, kBucketSmemInts >> lo_bits);
+    const size_t smem = sizeof(int) * ((size_t)warps << lo_bits);
+    if (smem > 48 * 1024)  // per device: set whenever it is needed (a few hundred ns)
+        DCRF_CUDA(cudaFuncSetAttribute(bucket_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(int) * kBucketSmemInts)));
+    bucket_csr_kernel<<<(unsigned)((int64_t)S << hi_bits), warps * 32, smem, s>>>(
+        grouped, hist.p, si, hi_bits, lo_bits, bary, d1, (int32_t)E, (int32_t)M, csr_start, csr_pix, csr_w);
+    DCRF_LAUNCHED();
+    return true;
+}
 
 void exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
     scan_rec(in, out, n, true, s);
