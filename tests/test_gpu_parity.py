@@ -289,6 +289,42 @@ def test_uniform_batch_shares_the_gaussian_lattice(mods):
         assert np.abs(o.inference(5) - Qb[i]).max() <= Q_TOL
 
 
+@pytest.mark.parametrize("arith", ["fma", "strict"])
+def test_mixed_batch_builds_the_gaussian_lattice_once_per_size(mods, arith):
+    """A batch with repeated sizes among distinct ones (PASCAL VOC val: 500x375, 500x333, 375x500, ...):
+    the position-only lattice is built once per DISTINCT size and replicated with per-image id shifts.
+    Every image must export exactly the oracle's lattice (keys, offsets, barycentric bits, neighbours,
+    norm) and Q must match image by image -- bit for bit in the strict reference arithmetic."""
+    O, G, S = mods
+    sizes = [(60, 44), (37, 52), (60, 44), (41, 41), (37, 52), (60, 44), (64, 30)]
+    L = 7
+    imgs = [S.natural_image(h, w, 50 + i) for i, (w, h) in enumerate(sizes)]
+    Us = [S.random_unary(L, w * h, 50 + i) for i, (w, h) in enumerate(sizes)]
+    gb = G.DenseCRFBatch(sizes, L)
+    gb.set_arithmetic(arith)
+    gb.setUnaryEnergy(Us)
+    gb.addPairwiseGaussian(sxy=3, compat=3)
+    gb.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs, compat=10)
+    Qb = gb.inference(5)
+    for i, (w, h) in enumerate(sizes):
+        o = O.DenseCRF2D(w, h, L)
+        o.setUnaryEnergy(Us[i])
+        o.addPairwiseGaussian(sxy=3, compat=3)
+        o.addPairwiseBilateral(sxy=40, srgb=13, rgbim=imgs[i], compat=10)
+        for k in range(2):
+            eo, eg = o.lattice(k), gb.lattice_export(k, image=i)
+            assert eo.M == eg["M"]
+            assert np.array_equal(eo.keys, eg["keys"]) and np.array_equal(eo.offsets, eg["offsets"])
+            assert np.array_equal(eo.neighbours, eg["neighbours"])
+            assert np.array_equal(eo.bary.view(np.uint32), eg["bary"].view(np.uint32))
+            np.testing.assert_allclose(eg["norm"], o.norm(k), rtol=2e-6, atol=0)
+        Qo = o.inference(5)
+        if arith == "strict":
+            assert np.array_equal(Qo.view(np.uint32), Qb[i].view(np.uint32))
+        else:
+            assert np.abs(Qo - Qb[i]).max() <= Q_TOL
+
+
 @pytest.mark.parametrize("terms", ["gauss", "bilat", "gauss+bilat+bilat", "bilat+gauss", "energy3d"])
 def test_other_term_combinations(mods, terms):
     """Anything but (Gaussian, bilateral) takes the generic fast slice: one term, three terms,

@@ -446,24 +446,52 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         DCRF_CUDA(cudaStreamSynchronize(s));
     }
     // A lattice whose features depend on the pixel position only (the Gaussian kernel) is the same
-    // for every image of a given size: when all images of the batch have one size it is built (and
-    // its norm filtered) ONCE for a single image and replicated with per-image id offsets.
-    bool uniform = fs.mode == 0 && h->geom.B > 1;
-    for (int b = 1; uniform && b < h->geom.B; b++)
-        uniform = h->geom.w[b] == h->geom.w[0] && h->geom.h[b] == h->geom.h[0];
-    BatchGeom one = h->geom;
-    if (uniform) {
-        one.B = 1;
-        one.Ntot = h->geom.pix_start[1];
-        one.w.resize(1);
-        one.h.resize(1);
-        one.pix_start.resize(2);  // device arrays are shared: their first entries describe image 0
+    // for every image of a given size: it is built (and its norm filtered) ONCE per distinct size of
+    // the batch and replicated with per-image id offsets (one size: bench.py's batches; a handful of
+    // sizes: a batch of PASCAL VOC val images).
+    std::vector<int> src(h->geom.B, 0);
+    BatchGeom ug;   // the distinct sizes, in order of first appearance
+    DevBuf<int> ug_w, ug_h, ug_ps;
+    std::vector<int> ug_ps32;
+    bool shared = false;
+    if (fs.mode == 0 && h->geom.B > 1) {
+        std::map<std::pair<int, int>, int> seen;
+        for (int b = 0; b < h->geom.B; b++) {
+            auto key = std::make_pair(h->geom.w[b], h->geom.h[b]);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (int)ug.w.size()).first;
+                ug.w.push_back(key.first);
+                ug.h.push_back(key.second);
+            }
+            src[b] = it->second;
+        }
+        shared = (int)ug.w.size() < h->geom.B;
     }
-    const BatchGeom &bg = uniform ? one : h->geom;
+    if (shared) {
+        ug.B = (int)ug.w.size();
+        ug.pix_start.assign(ug.B + 1, 0);
+        ug_ps32.assign(ug.B + 1, 0);
+        for (int u = 0; u < ug.B; u++) {
+            ug.pix_start[u + 1] = ug.pix_start[u] + (int64_t)ug.w[u] * ug.h[u];
+            ug_ps32[u + 1] = (int)ug.pix_start[u + 1];
+        }
+        ug.Ntot = ug.pix_start[ug.B];
+        ug_w.alloc(ug.B, s);
+        ug_h.alloc(ug.B, s);
+        ug_ps.alloc(ug.B + 1, s);
+        DCRF_CUDA(copy_h2d(ug_w.p, ug.w.data(), sizeof(int) * ug.B, s));
+        DCRF_CUDA(copy_h2d(ug_h.p, ug.h.data(), sizeof(int) * ug.B, s));
+        DCRF_CUDA(copy_h2d(ug_ps.p, ug_ps32.data(), sizeof(int) * (ug.B + 1), s));
+        ug.d_w = ug_w.p;
+        ug.d_h = ug_h.p;
+        ug.d_pix_start = ug_ps.p;
+    }
+    const BatchGeom &bg = shared ? ug : h->geom;
     Lattice single;
-    Lattice &lat = uniform ? single : p->lat;
+    Lattice &lat = shared ? single : p->lat;
     DevBuf<float> norm_single;
-    DevBuf<float> &norm = uniform ? norm_single : p->norm;
+    DevBuf<float> &norm = shared ? norm_single : p->norm;
     build_lattice(bg, fs, lat, s);
     // A.5: norm = filter(ones) through the value_size = 1 path
     if (ntype != DCRF_NO_NORMALIZATION) {
@@ -475,9 +503,10 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
         ProfScope prof(DCRF_K_BUILD_CSR, lat.d, s);
         pack_tables(h, lat, ntype, norm.p, s);
     }
-    if (uniform) {
+    if (shared) {
         if (norm.p) p->norm.alloc(Ntot, s);
-        launch_replicate_lattice(single, norm.p, h->geom.B, bg.Ntot, p->lat, p->norm.p, s);
+        // (the uploads of ug's arrays completed before build_lattice's host synchronisation returned)
+        launch_replicate_lattice(single, ug, norm.p, h->geom, src, p->lat, p->norm.p, s);
     }
     p->valA.alloc((size_t)p->lat.M * Lp, s);
     p->valB.alloc((size_t)p->lat.M * Lp, s);

@@ -166,7 +166,7 @@ struct Lattice {
     // instead of synchronising the stream before they go out of scope)
     std::vector<int64_t> h_tab_start, h_tab2_start;
     std::vector<int> h_tab_mask, h_tab2_mask;
-    std::vector<int32_t> h_seg, h_tile;
+    std::vector<int32_t> h_seg, h_tile, h_rep;
     DevBuf<int32_t> offset;        // [E] vertex id of entry e = p*(d+1)+r
     DevBuf<float> bary;            // [E]
     DevBuf<int2> neigh;            // [(d+1) * M] (n1, n2), -1 = absent
@@ -188,10 +188,11 @@ struct Lattice {
 };
 
 void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
-// `one` (lattice of a single image with n_img pixels, fast tables packed) -> `out`: the same lattice
-// for B identical images laid back to back, ids shifted per image (b * M, b * n_img, b * E).
-void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, int64_t n_img, Lattice &out,
-                              float *norm_out, cudaStream_t s);
+// `one`: lattice (packed tables included) over the DISTINCT image sizes `og` of the batch `g`; image b of
+// the batch is unique image src[b].  `out`: the same lattice for every image of the batch laid back to
+// back, pixel / vertex / entry ids shifted per image.
+void launch_replicate_lattice(const Lattice &one, const BatchGeom &og, const float *norm_one, const BatchGeom &g,
+                              const std::vector<int> &src, Lattice &out, float *norm_out, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
 // filtering + mean field (filter.cu)

@@ -682,73 +682,99 @@ void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaS
 
 
 // ---------------------------------------------------------------------------------------------
-// replication of a geometry-only lattice over the B identical images of a batch
+// replication of a geometry-only lattice: `one` was built over the DISTINCT image sizes of a batch,
+// image b of the batch is a copy of unique image src[b] with its pixel / vertex / entry ids shifted
 // ---------------------------------------------------------------------------------------------
 namespace {
-// grid (ceil(n / 256), B): out[b * n + i] = in[i] (+ b * shift when in[i] >= 0)
-__global__ void __launch_bounds__(kThreads) rep_i32_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out,
-                                                           int64_t n, int64_t shift) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    const int32_t v = in[i];
-    out[(int64_t)blockIdx.y * n + i] = v >= 0 ? (int32_t)(v + (int64_t)blockIdx.y * shift) : v;
+// where image b's copy comes from and goes to (pixels, vertices; entries = pixels * (d+1))
+struct RepImg {
+    int src_pix, dst_pix, n_pix;
+    int src_vert, dst_vert, n_vert;
+};
+
+// what to add to an id stored in the array: nothing, the vertex shift, the pixel shift or the entry shift
+enum { kShiftNone = 0, kShiftVert = 1, kShiftPix = 2, kShiftEnt = 3 };
+// which index space the array lives in
+enum { kOverPix = 0, kOverVert = 1, kOverEnt = 2 };
+
+__device__ __forceinline__ int rep_shift(const RepImg &r, int kind, int d1) {
+    if (kind == kShiftVert) return r.dst_vert - r.src_vert;
+    if (kind == kShiftPix) return r.dst_pix - r.src_pix;
+    if (kind == kShiftEnt) return (r.dst_pix - r.src_pix) * d1;
+    return 0;
 }
-// pairs (id, payload): x shifted, y copied
-__global__ void __launch_bounds__(kThreads) rep_i2_kernel(const int2 *__restrict__ in, int2 *__restrict__ out,
-                                                          int64_t n, int64_t shift_x, int64_t shift_y) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    int2 v = in[i];
-    if (v.x >= 0) v.x = (int32_t)(v.x + (int64_t)blockIdx.y * shift_x);
-    if (shift_y && v.y >= 0) v.y = (int32_t)(v.y + (int64_t)blockIdx.y * shift_y);
-    out[(int64_t)blockIdx.y * n + i] = v;
+__device__ __forceinline__ void rep_range(const RepImg &r, int over, int d1, int64_t &src, int64_t &dst, int64_t &n) {
+    if (over == kOverVert) {
+        src = r.src_vert; dst = r.dst_vert; n = r.n_vert;
+    } else if (over == kOverEnt) {
+        src = (int64_t)r.src_pix * d1; dst = (int64_t)r.dst_pix * d1; n = (int64_t)r.n_pix * d1;
+    } else {
+        src = r.src_pix; dst = r.dst_pix; n = r.n_pix;
+    }
 }
-// packed reference entries (pixel, w, norm, -): pixel shifted, payload copied
-__global__ void __launch_bounds__(kThreads) rep_i4x_kernel(const int4 *__restrict__ in, int4 *__restrict__ out,
-                                                           int64_t n, int64_t shift_x) {
+
+// grid (ceil(max count / 256), B).  T = int32 / float (W = 1), int2 (W = 2: x shifted), int4 (W = 4: x
+// shifted); ids < 0 (absent neighbour) are never shifted.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) rep_kernel(const T *__restrict__ in, T *__restrict__ out,
+                                                       const RepImg *__restrict__ tab, int over, int shift_kind,
+                                                       int d1) {
+    const RepImg r = tab[blockIdx.y];
+    int64_t src, dst, n;
+    rep_range(r, over, d1, src, dst, n);
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
-    int4 v = in[i];
-    v.x = (int32_t)(v.x + (int64_t)blockIdx.y * shift_x);
-    out[(int64_t)blockIdx.y * n + i] = v;
+    T v = in[src + i];
+    if (shift_kind != kShiftNone) {
+        int *x = reinterpret_cast<int *>(&v);  // first word: the id
+        if (*x >= 0) *x += rep_shift(r, shift_kind, d1);
+    }
+    out[dst + i] = v;
+}
+// neighbour table [axis][vertex] of (n1, n2): both ids shifted
+__global__ void __launch_bounds__(kThreads) rep_neigh_kernel(const int2 *__restrict__ in, int2 *__restrict__ out,
+                                                             const RepImg *__restrict__ tab, int64_t M_in,
+                                                             int64_t M_out, int d1) {
+    const RepImg r = tab[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)r.n_vert * d1) return;
+    const int j = (int)(i / r.n_vert);
+    const int64_t v = i - (int64_t)j * r.n_vert;
+    int2 nb = in[(int64_t)j * M_in + r.src_vert + v];
+    const int sh = r.dst_vert - r.src_vert;
+    if (nb.x >= 0) nb.x += sh;
+    if (nb.y >= 0) nb.y += sh;
+    out[(int64_t)j * M_out + r.dst_vert + v] = nb;
 }
 __global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
-__global__ void __launch_bounds__(kThreads) rep_f32_kernel(const float *__restrict__ in, float *__restrict__ out,
-                                                           int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) out[(int64_t)blockIdx.y * n + i] = in[i];
-}
-__global__ void __launch_bounds__(kThreads) rep_i4_kernel(const int4 *__restrict__ in, int4 *__restrict__ out,
-                                                          int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i < n) out[(int64_t)blockIdx.y * n + i] = in[i];
-}
-// neighbour table is [axis][vertex]: out[(j * B*M) + b*M + v]
-__global__ void __launch_bounds__(kThreads) rep_neigh_kernel(const int2 *__restrict__ in, int2 *__restrict__ out,
-                                                             int64_t M, int B, int d1) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= M * d1) return;
-    const int j = (int)(i / M);
-    const int64_t v = i - (int64_t)j * M;
-    int2 nb = in[i];
-    const int64_t sh = (int64_t)blockIdx.y * M;
-    if (nb.x >= 0) nb.x = (int32_t)(nb.x + sh);
-    if (nb.y >= 0) nb.y = (int32_t)(nb.y + sh);
-    out[(int64_t)j * M * B + sh + v] = nb;
-}
 }  // namespace
 
-void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, int64_t n_img, Lattice &out,
-                              float *norm_out, cudaStream_t s) {
+void launch_replicate_lattice(const Lattice &one, const BatchGeom &og, const float *norm_one, const BatchGeom &g,
+                              const std::vector<int> &src, Lattice &out, float *norm_out, cudaStream_t s) {
     const int d1 = one.d + 1;
-    const int64_t M = one.M, E = one.E;
+    const int B = g.B;
     ProfScope prof(DCRF_K_BUILD_REPL, one.d, s);
-    DCRF_REQUIRE(E * B < (int64_t)2147483000, DCRF_EINVAL, "batch too large: N*(d+1) must stay below 2^31");
+    DCRF_REQUIRE(g.Ntot * d1 < (int64_t)2147483000, DCRF_EINVAL, "batch too large: N*(d+1) must stay below 2^31");
     out.d = one.d;
-    out.M = M * B;
-    out.E = E * B;
-    out.vert_start.resize(B + 1);
-    for (int b = 0; b <= B; b++) out.vert_start[b] = M * b;
+    out.E = g.Ntot * d1;
+    out.vert_start.assign(B + 1, 0);
+    static_assert(sizeof(RepImg) == 6 * sizeof(int32_t), "RepImg is six ints");
+    out.h_rep.assign((size_t)B * 6, 0);  // staging of an asynchronous upload: lives with the lattice
+    RepImg *tab = reinterpret_cast<RepImg *>(out.h_rep.data());
+    int64_t max_pix = 1, max_vert = 1;
+    for (int b = 0; b < B; b++) {
+        const int u = src[b];
+        const int64_t mv = one.vert_start[u + 1] - one.vert_start[u];
+        out.vert_start[b + 1] = out.vert_start[b] + mv;
+        tab[b] = RepImg{(int)og.pix_start[u], (int)g.pix_start[b], (int)(og.pix_start[u + 1] - og.pix_start[u]),
+                        (int)one.vert_start[u], (int)out.vert_start[b], (int)mv};
+        max_pix = std::max<int64_t>(max_pix, tab[b].n_pix);
+        max_vert = std::max<int64_t>(max_vert, mv);
+    }
+    out.M = out.vert_start[B];
+    DevBuf<RepImg> d_tab;
+    d_tab.alloc(B, s);
+    DCRF_CUDA(copy_h2d(d_tab.p, tab, sizeof(RepImg) * B, s));
     out.offset.alloc(out.E, s);
     out.bary.alloc(out.E, s);
     out.neigh.alloc((size_t)out.M * d1, s);
@@ -760,38 +786,39 @@ void launch_replicate_lattice(const Lattice &one, const float *norm_one, int B, 
     out.table_mode = one.table_mode;
     out.long_row_cap = one.long_row_cap;
     auto grid = [&](int64_t n) { return dim3(ceil_div(n, kThreads), B); };
-    rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.offset.p, out.offset.p, E, M);
+    const dim3 ge = grid(max_pix * d1), gv = grid(max_vert), gp = grid(max_pix);
+    rep_kernel<int32_t><<<ge, kThreads, 0, s>>>(one.offset.p, out.offset.p, d_tab.p, kOverEnt, kShiftVert, d1);
     DCRF_LAUNCHED();
-    rep_f32_kernel<<<grid(E), kThreads, 0, s>>>(one.bary.p, out.bary.p, E);
+    rep_kernel<float><<<ge, kThreads, 0, s>>>(one.bary.p, out.bary.p, d_tab.p, kOverEnt, kShiftNone, d1);
     DCRF_LAUNCHED();
-    rep_neigh_kernel<<<grid(M * d1), kThreads, 0, s>>>(one.neigh.p, out.neigh.p, M, B, d1);
+    rep_neigh_kernel<<<grid(max_vert * d1), kThreads, 0, s>>>(one.neigh.p, out.neigh.p, d_tab.p, one.M, out.M, d1);
     DCRF_LAUNCHED();
-    rep_i4_kernel<<<grid(M), kThreads, 0, s>>>(reinterpret_cast<const int4 *>(one.vkeys.p),
-                                                reinterpret_cast<int4 *>(out.vkeys.p), M);
+    rep_kernel<int4><<<gv, kThreads, 0, s>>>(reinterpret_cast<const int4 *>(one.vkeys.p),
+                                            reinterpret_cast<int4 *>(out.vkeys.p), d_tab.p, kOverVert, kShiftNone, d1);
     DCRF_LAUNCHED();
-    // csr_start has M+1 entries per image; entry M of image b coincides with entry 0 of image b+1
-    rep_i32_kernel<<<grid(M), kThreads, 0, s>>>(one.csr_start.p, out.csr_start.p, M, E);
+    // row starts: the rows of an image are the entries of that image, so they move by its entry shift
+    rep_kernel<int32_t><<<gv, kThreads, 0, s>>>(one.csr_start.p, out.csr_start.p, d_tab.p, kOverVert, kShiftEnt, d1);
     DCRF_LAUNCHED();
     set_i32_kernel<<<1, 1, 0, s>>>(out.csr_start.p + out.M, (int32_t)out.E);
     DCRF_LAUNCHED();
-    rep_i32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_pix.p, out.csr_pix.p, E, n_img);
+    rep_kernel<int32_t><<<ge, kThreads, 0, s>>>(one.csr_pix.p, out.csr_pix.p, d_tab.p, kOverEnt, kShiftPix, d1);
     DCRF_LAUNCHED();
-    rep_f32_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_w.p, out.csr_w.p, E);
+    rep_kernel<float><<<ge, kThreads, 0, s>>>(one.csr_w.p, out.csr_w.p, d_tab.p, kOverEnt, kShiftNone, d1);
     DCRF_LAUNCHED();
-    rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.ent.p, out.ent.p, E, M, 0);
+    rep_kernel<int2><<<ge, kThreads, 0, s>>>(one.ent.p, out.ent.p, d_tab.p, kOverEnt, kShiftVert, d1);
     DCRF_LAUNCHED();
     if (one.table_mode == kTablesRef) {
         out.csr_ent4.alloc(out.E, s);
-        rep_i4x_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent4.p, out.csr_ent4.p, E, n_img);
+        rep_kernel<int4><<<ge, kThreads, 0, s>>>(one.csr_ent4.p, out.csr_ent4.p, d_tab.p, kOverEnt, kShiftPix, d1);
     } else {
         out.csr_ent.alloc(out.E, s);
-        rep_i2_kernel<<<grid(E), kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, E, n_img, 0);
+        rep_kernel<int2><<<ge, kThreads, 0, s>>>(one.csr_ent.p, out.csr_ent.p, d_tab.p, kOverEnt, kShiftPix, d1);
     }
     DCRF_LAUNCHED();
     if (one.row_counter.p) out.row_counter.alloc(2, s);
     launch_find_long_rows(out, s);
     if (norm_one && norm_out) {
-        rep_f32_kernel<<<grid(n_img), kThreads, 0, s>>>(norm_one, norm_out, n_img);
+        rep_kernel<float><<<gp, kThreads, 0, s>>>(norm_one, norm_out, d_tab.p, kOverPix, kShiftNone, d1);
         DCRF_LAUNCHED();
     }
 }
