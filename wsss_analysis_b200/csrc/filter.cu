@@ -207,8 +207,7 @@ __device__ __forceinline__ float ent_norm(const int4 e) { return __int_as_float(
 // schedule: bit-deterministic run to run.
 constexpr int kSplatChunk = 32;
 // Rows longer than this (flat image regions collapse the bilateral lattice to a few vertices with
-// thousands of entries each) are cut: one lane group sums the first kSplatLongRow entries here, a
-// whole warp per row sums the tail in splat_tail_warp_kernel.
+// thousands of entries each) leave the queue: whole warps sum them, one row per warp (splat_long_rows_body).
 constexpr int kSplatLongRow = 256;
 constexpr int kSmallLatticeEntries = 4000000;  // below this many entries a lattice counts as "small" (see launch_pack_fast_tables)
 #ifndef DCRF_TUNE_SPLAT_REF_MINB
@@ -281,9 +280,9 @@ __device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_
             int b1 = __shfl_sync(FULL, bounds, (rel + 1) & 31);
             if (rel + 1 == q_end - q_base) b1 = bound_last;
             if (need) {
-                nv = take ? row : -1;
+                nv = (take && b1 - b0 <= long_cap) ? row : -1;  // long rows: summed by whole warps (splat_long_rows_body)
                 ns = b0;
-                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;  // the rest of a long row: splat_tail_warp_kernel
+                ns1 = b1;
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
@@ -308,15 +307,6 @@ __device__ __forceinline__ void splat_fast_body(const int32_t *__restrict__ csr_
         for (int i = 0; i < SB; i++) e_cur[i] = e_next[i];
         if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
     }
-}
-
-template <int G, int SB, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
-                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-                                                              const float4 *__restrict__ Q4,
-                                                              float4 *__restrict__ val4, int M, int g_rt,
-                                                              int *__restrict__ row_counter, int long_cap, int chunk) {
-    splat_fast_body<G, SB, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, row_counter, long_cap, chunk);
 }
 
 // Same schedule with COOPERATIVE entry loads: every warp-level load request costs the LSU a fixed
@@ -388,9 +378,9 @@ __device__ __forceinline__ void splat_coop_body(const int32_t *__restrict__ csr_
             int b1 = __shfl_sync(FULL, bounds, (rel + 1) & 31);
             if (rel + 1 == q_end - q_base) b1 = bound_last;
             if (need) {
-                nv = take ? row : -1;
+                nv = (take && b1 - b0 <= long_cap) ? row : -1;  // long rows: summed by whole warps (splat_long_rows_body)
                 ns = b0;
-                ns1 = (b1 - b0 > long_cap) ? b0 + long_cap : b1;
+                ns1 = b1;
             }
             q_next = min(q_end, q_next + __popc(need_mask));
         }
@@ -421,15 +411,6 @@ __device__ __forceinline__ void splat_coop_body(const int32_t *__restrict__ csr_
         for (int b = 0; b < NB; b++) e_cur[b] = e_next[b];
         if (!__ballot_sync(FULL, v >= 0) && exhausted) break;
     }
-}
-
-template <int G, int NB, int MINB, bool REF>
-__global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
-                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-                                                              const float4 *__restrict__ Q4,
-                                                              float4 *__restrict__ val4, int M,
-                                                              int *__restrict__ row_counter, int long_cap, int chunk) {
-    splat_coop_body<G, NB, REF>(csr_start, csr_ent, Q4, val4, M, row_counter, long_cap, chunk);
 }
 
 // rows with more than long_cap entries (found at build time, any order: rows are independent)
@@ -513,17 +494,20 @@ __global__ void __launch_bounds__(kThreads) splat_short_kernel(const int32_t *__
     splat_short_body<G, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, blockIdx.x);
 }
 
-// val[v] += sum of the entries beyond the first long_cap of each long row v, one WARP per row (round 2;
-// round 1 used a whole CTA per row with a shared-memory tree).  Warps claim long rows from a counter; per round the warp loads 32/g * g
-// consecutive entries with ONE coalesced request, lane group k sums entries [k g, (k + 1) g) of the round
-// (g gathers in flight), and the groups' partial sums are added in group order -- a fixed association, so the result is deterministic
-// (though not the sequential order of the specification).  With whole CTAs per row and a shared-memory
-// tree, lattices with MANY moderately long rows (histology: 30 % of the entries in rows of 256-1600
-// entries) spent most of the splat in this tail: cap 256 / 64 / 32 gave 369 / 615 / 782 us for the
-// bilateral splat of 16 HistoSegNet 321^2 images; with this kernel the cut can sit where the main
-// kernel's one-row-per-lane-group schedule stays balanced (see profiles/README.md).
+// Rows with more than long_cap entries (flat image regions collapse the bilateral lattice to a few vertices
+// with thousands of entries each; histology: 30 % of the entries sit in rows of 256-1600) are summed by
+// whole WARPS, one row per warp, claimed from a counter: per round the warp loads 32/g * g consecutive
+// entries with ONE coalesced request, lane group k sums entries [k g, (k + 1) g) of the round (g gathers in
+// flight), and the groups' partial sums are added in group order -- a fixed association, so the result is
+// deterministic (though not the sequential order of the specification; DCRF_ARITH_STRICT has no long rows).
+// Every warp of the splat kernel does this FIRST (longest work first), then joins the row queue, which
+// skips these rows -- round 2 ran a separate tail kernel after the queue kernel for the entries beyond
+// the cut (a ~7 us launch on the critical path of every iteration of a small problem).
+// History of the cut: with whole CTAs per row and a shared-memory tree (round 1) cap 256 / 64 / 32 gave
+// 369 / 615 / 782 us for the bilateral splat of 16 HistoSegNet 321^2 images; with warps per row the cut can
+// sit where the queue's one-row-per-lane-group schedule stays balanced (see profiles/README.md).
 template <int G, bool REF>
-__device__ __forceinline__ void splat_tail_warp_body(
+__device__ __forceinline__ void splat_long_rows_body(
     const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
     const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
     const int *__restrict__ n_long, int g_rt, int long_cap, int *__restrict__ counter) {
@@ -536,13 +520,14 @@ __device__ __forceinline__ void splat_tail_warp_body(
     const int per_round = gpw * g;  // entries per warp round: group k takes entries [k g, (k + 1) g) of the round
     const int gbase = (sub * g) & 31;
     const int n = *n_long;
+    if (n == 0) return;
     for (;;) {
         int i = 0;
         if (lane == 0) i = atomicAdd(counter, 1);
         i = __shfl_sync(FULL, i, 0);
         if (i >= n) break;
         const int v = long_rows[i];
-        const int s0 = csr_start[v] + long_cap, s1 = csr_start[v + 1];
+        const int s0 = csr_start[v], s1 = csr_start[v + 1];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         // one coalesced entry load per round (lane l: entry l of the round), pairs broadcast inside the group
         Ent e_cur = (on && s0 + lane < s1) ? __ldg(csr_ent + s0 + lane) : zero_ent(Ent());
@@ -586,20 +571,43 @@ __device__ __forceinline__ void splat_tail_warp_body(
             tot.z += __shfl_sync(FULL, acc.z, k * g + c);
             tot.w += __shfl_sync(FULL, acc.w, k * g + c);
         }
-        if (on && sub == 0) {
-            float4 o = val4[(unsigned)v * g + c];
-            o.x += tot.x; o.y += tot.y; o.z += tot.z; o.w += tot.w;
-            val4[(unsigned)v * g + c] = o;
-        }
+        if (on && sub == 0) val4[(unsigned)v * g + c] = tot;
     }
 }
 
-template <int G, bool REF>
-__global__ void __launch_bounds__(kThreads) splat_tail_warp_kernel(
-    const int32_t *__restrict__ csr_start, const typename CsrEnt<REF>::type *__restrict__ csr_ent,
-    const float4 *__restrict__ Q4, float4 *__restrict__ val4, const int32_t *__restrict__ long_rows,
-    const int *__restrict__ n_long, int g_rt, int long_cap, int *__restrict__ counter) {
-    splat_tail_warp_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, counter);
+// The splat kernels.  The first kLongRowBlocks CTAs of the grid (scheduled first) sum the long rows, whole
+// warps per row; all others run the row queue, which skips those rows: one launch, the longest work
+// starts first and runs next to the queue.  With no long rows the extra CTAs exit at once.  (Letting
+// the queue CTAs help with leftover long rows afterwards costs the queue loop its spill-free 48 registers.)
+constexpr int kLongRowBlocks = 4 * kNumSMs;
+template <int G, int SB, bool REF>
+__global__ void __launch_bounds__(kThreads) splat_fast_kernel(const int32_t *__restrict__ csr_start,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M, int g_rt,
+                                                              int *__restrict__ row_counter, int long_cap, int chunk,
+                                                              const int32_t *__restrict__ long_rows,
+                                                              const int *__restrict__ n_long) {
+    if (blockIdx.x < kLongRowBlocks) {
+        splat_long_rows_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, g_rt, long_cap, row_counter + 1);
+        return;
+    }
+    splat_fast_body<G, SB, REF>(csr_start, csr_ent, Q4, val4, M, g_rt, row_counter, long_cap, chunk);
+}
+
+template <int G, int NB, int MINB, bool REF>
+__global__ void __launch_bounds__(kThreads, MINB) splat_coop_kernel(const int32_t *__restrict__ csr_start,
+                                                              const typename CsrEnt<REF>::type *__restrict__ csr_ent,
+                                                              const float4 *__restrict__ Q4,
+                                                              float4 *__restrict__ val4, int M,
+                                                              int *__restrict__ row_counter, int long_cap, int chunk,
+                                                              const int32_t *__restrict__ long_rows,
+                                                              const int *__restrict__ n_long) {
+    if (blockIdx.x < kLongRowBlocks) {
+        splat_long_rows_body<G, REF>(csr_start, csr_ent, Q4, val4, long_rows, n_long, G, long_cap, row_counter + 1);
+        return;
+    }
+    splat_coop_body<G, NB, REF>(csr_start, csr_ent, Q4, val4, M, row_counter, long_cap, chunk);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1474,7 +1482,7 @@ __global__ void kl_final_kernel(const double *__restrict__ partial, double *__re
 
 // ---------------------------------------------------------------------------------------------
 // Persistent mean field for SMALL problems (one VOC image, a batch of 41x41 SEC maps): the whole of
-// `inference(n)` -- Q0 = softmax(-U), then n x [splat, (long-row tails), d+1 blurs, fused slice] -- as
+// `inference(n)` -- Q0 = softmax(-U), then n x [splat, d+1 blurs, fused slice] -- as
 // ONE cooperative launch with grid barriers between the phases.  With a kernel per phase such
 // problems are launch-latency bound (~16 launches of 5-20 us per iteration); here an iteration costs
 // its work plus ~9 grid barriers.  The phases run the same device bodies as the stand-alone kernels
@@ -1497,7 +1505,7 @@ struct MfArgs {
     float4 *Q4;
     unsigned Ntot;
     int L, g, n_iter;
-    int *counters;  // [2 * n_iter * n_terms] row dispensers of the splats and of their long-row tails, zeroed before the launch
+    int *counters;  // [2 * n_iter * n_terms] row dispensers of the splats and of their long rows, zeroed before the launch
 };
 
 template <int G, bool REF>
@@ -1521,7 +1529,6 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
     for (int k = 0; k < nt; k++) dmax = max(dmax, a.term[k].d);
     for (int it = 0; it < a.n_iter; it++) {
         // splat of every term (dynamic row queues: no barrier between the terms)
-        bool any_long = false;
         for (int k = 0; k < nt; k++) {
             const MfTerm &t = a.term[k];
             int *ctr = a.counters + it * nt + k;
@@ -1533,6 +1540,8 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
                     splat_short_body<G, REF>(t.csr_start, ents, a.Q4, v4, t.M, g, vb);
                 continue;
             }
+            splat_long_rows_body<G, REF>(t.csr_start, ents, a.Q4, v4, t.long_rows, t.n_long, g, t.long_cap,
+                                         a.counters + (a.n_iter + it) * nt + k);
             if (G >= 4 && G <= 8) {
                 splat_coop_body<(G >= 4 && G <= 8) ? G : 4, 1, REF>(t.csr_start, ents, a.Q4, v4, t.M, ctr, t.long_cap);
             } else if (t.long_hint) {
@@ -1540,19 +1549,8 @@ __global__ void __launch_bounds__(kThreads) mean_field_persistent_kernel(const M
             } else {
                 splat_fast_body<G, kSplatBatch, REF>(t.csr_start, ents, a.Q4, v4, t.M, g, ctr, t.long_cap);
             }
-            any_long = any_long || *t.n_long > 0;  // written at build time: the same value in every CTA
         }
         grid.sync();
-        if (any_long) {
-            for (int k = 0; k < nt; k++) {
-                const MfTerm &t = a.term[k];
-                if (t.short_rows) continue;   // the static kernel summed whole rows
-                splat_tail_warp_body<G, REF>(t.csr_start, reinterpret_cast<const Ent *>(t.csr_ent), a.Q4,
-                                             reinterpret_cast<float4 *>(t.valA), t.long_rows, t.n_long, g, t.long_cap,
-                                             a.counters + (a.n_iter + it) * nt + k);
-            }
-            grid.sync();
-        }
         // blurs: axis j of every term that has it, ping-pong A <-> B
         for (int j = 0; j <= dmax; j++) {
             for (int k = 0; k < nt; k++) {
@@ -1705,7 +1703,7 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         DCRF_LAUNCHED();
         return;
     }
-    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, 2 * sizeof(int), s));  // [0] rows, [1] long-row tails
+    DCRF_CUDA(cudaMemsetAsync(lat.row_counter.p, 0, 2 * sizeof(int), s));  // [0] rows, [1] long rows
     ProfScope prof(DCRF_K_SPLAT, lat.d, s);
     // entries per trip: long rows (Gaussian lattice, ~23 entries) amortise the loop overhead over 8
     // entries, short skewed rows (bilateral lattice, median 6) waste fewer predicated slots with 4
@@ -1720,10 +1718,9 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         constexpr int MB = (REF && kSplatRefMinBlocks) ? kSplatRefMinBlocks : MINB;                         \
         static const int per_sm = resident_blocks_per_sm(splat_coop_kernel<GG, 1, MB, REF>);                \
         const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);   \
-        splat_coop_kernel<GG, 1, MB, REF><<<nb, kThreads, 0, s>>>(                                         \
-            lat.csr_start.p, ents, q4, v4, (int)lat.M, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb)); \
-        splat_tail_warp_kernel<GG, REF><<<kNumSMs * 4, kThreads, 0, s>>>(                                  \
-            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap, lat.row_counter.p + 1);  \
+        splat_coop_kernel<GG, 1, MB, REF><<<nb + kLongRowBlocks, kThreads, 0, s>>>(                                       \
+            lat.csr_start.p, ents, q4, v4, (int)lat.M, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb),  \
+            lat.long_rows.p, lat.n_long.p);                                                                \
     } break;
         switch (g) {
             DCRF_COOP_LAUNCH(4, 5)
@@ -1734,7 +1731,6 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         }
 #undef DCRF_COOP_LAUNCH
         DCRF_LAUNCHED();
-        g_launches.fetch_add(1);
         return;
     }
     DCRF_DISPATCH_G(g, {
@@ -1742,20 +1738,18 @@ static void launch_splat_packed(const Lattice &lat, const float *Q, float *val, 
         if (long_rows) {
             static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, 8, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
-            splat_fast_kernel<G, 8, REF><<<nb, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4, (int)lat.M, g,
-                                                                lat.row_counter.p, cap, splat_chunk(lat.M, g, nb));
+            splat_fast_kernel<G, 8, REF><<<nb + kLongRowBlocks, kThreads, 0, s>>>(lat.csr_start.p, ents, q4, v4, (int)lat.M, g,
+                                                                lat.row_counter.p, cap, splat_chunk(lat.M, g, nb),
+                                                                lat.long_rows.p, lat.n_long.p);
         } else {
             static const int per_sm = resident_blocks_per_sm(splat_fast_kernel<G, kSplatBatch, REF>);
             const int nb = (int)std::min<int64_t>(ceil_div(lat.M * g, kThreads), (int64_t)kNumSMs * per_sm);
-            splat_fast_kernel<G, kSplatBatch, REF><<<nb, kThreads, 0, s>>>(
-                lat.csr_start.p, ents, q4, v4, (int)lat.M, g, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb));
+            splat_fast_kernel<G, kSplatBatch, REF><<<nb + kLongRowBlocks, kThreads, 0, s>>>(
+                lat.csr_start.p, ents, q4, v4, (int)lat.M, g, lat.row_counter.p, cap, splat_chunk(lat.M, g, nb),
+                lat.long_rows.p, lat.n_long.p);
         }
-        // tail of very long rows (no-op grid when the lattice has none; the count lives on the device)
-        splat_tail_warp_kernel<G, REF><<<kNumSMs * 4, kThreads, 0, s>>>(
-            lat.csr_start.p, ents, q4, v4, lat.long_rows.p, lat.n_long.p, g, cap, lat.row_counter.p + 1);
     });
     DCRF_LAUNCHED();
-    g_launches.fetch_add(1);
 }
 
 void launch_splat_fast(const Lattice &lat, const float *Q, float *val, int Lp, cudaStream_t s) {

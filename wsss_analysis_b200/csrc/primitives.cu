@@ -285,29 +285,34 @@ namespace {
 // and a private set of per-vertex cursors; the cursors of (vertex, warp) start where the entries of
 // that vertex in the slices before w end, so every warp places its slice in order on its own, rank
 // among equal vertices inside a 32-entry round from __match_any_sync in lane order.  No block barrier
-// inside the placement loop.  Shared memory: warps * 2^lo_bits cursors (<= 64 KB: 8 warps up to 11 low
-// bits, 4 at 12, 2 at 13).
-constexpr int kBucketMaxLoBits = 13;
+// inside the placement loop.  Shared memory: warps * (vertices of the CTA) cursors, at most 32 KB.
+constexpr int kBucketMaxLoBits = 13;  // up to 2^13 vertices per bucket (vertex ids of an image: up to 23 bits)
+constexpr int kBucketCtaBits = 10;    // up to 2^10 vertices per CTA: 8 warps x 1024 cursors = 32 KB
 constexpr int kBucketMaxThreads = 256;
-constexpr int kBucketSmemInts = 16384;  // 64 KB
 
 __global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
     const uint2 *__restrict__ pairs, const int32_t *__restrict__ hist_scanned, SegInfo si, int hi_bits, int lo_bits,
-    const float *__restrict__ bary, int d1, int32_t E, int32_t M, int32_t *__restrict__ csr_start,
+    int vbits, const float *__restrict__ bary, int d1, int32_t E, int32_t M, int32_t *__restrict__ csr_start,
     int32_t *__restrict__ csr_pix, float *__restrict__ csr_w) {
-    extern __shared__ int cursor[];  // [warps][1 << lo_bits]: counts, then running output positions
+    extern __shared__ int cursor[];  // [warps][1 << (lo_bits - vbits)]: counts, then running output positions
     __shared__ int warp_sums[kBucketMaxThreads / 32];
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (blockIdx.x == 0 && tid == 0) csr_start[M] = E;
     const int radix = 1 << hi_bits;
-    const int seg = blockIdx.x >> hi_bits, digit = blockIdx.x & (radix - 1);
+    // Large images (2^lo_bits vertices per bucket would not fit the cursors): 2^vbits CTAs share a bucket,
+    // each owns a contiguous 2^(lo_bits - vbits) sub-range of its vertices, walks ALL entries of the bucket
+    // (L2 hits) and places the ones of its sub-range.
+    const int sub = blockIdx.x & ((1 << vbits) - 1);
+    const int bucket = blockIdx.x >> vbits;
+    const int seg = bucket >> hi_bits, digit = bucket & (radix - 1);
     const int kb = si.key_base[seg];
     const int Mb = si.key_base[seg + 1] - kb;
-    const int v0 = digit << lo_bits;  // first local vertex of the bucket
+    const int sbits = lo_bits - vbits;
+    const int v0 = (digit << lo_bits) + (sub << sbits);  // first local vertex of this CTA
     if (v0 >= Mb) return;
-    const int nv = min(1 << lo_bits, Mb - v0);
+    const int nv = min(1 << sbits, Mb - v0);
     int start, end;
     if (hi_bits > 0) {
         const int tiles = si.tile_base[seg + 1] - si.tile_base[seg];
@@ -318,8 +323,8 @@ __global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
         start = si.seg_start[seg];
         end = si.seg_start[seg + 1];
     }
-    const uint32_t vbase = (uint32_t)(kb + v0);
-    const int stride = 1 << lo_bits;
+    const uint32_t vbase = (uint32_t)(kb + v0);  // keys of this CTA: [vbase, vbase + nv); below: earlier sub-ranges
+    const int stride = 1 << sbits;
     for (int j = tid; j < nwarps * stride; j += nthreads) cursor[j] = 0;
     __syncthreads();
     // slice of this warp: whole 32-entry rounds, the last warp takes the remainder
@@ -328,18 +333,35 @@ __global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
     const int s0 = min(n, warp * rounds_per_warp * 32);
     const int s1 = (warp == nwarps - 1) ? n : min(n, s0 + rounds_per_warp * 32);
     int *mine = cursor + warp * stride;
-    // counts of the slice (4 loads in flight per lane)
+    // counts of the slice (4 loads in flight per lane); entries of earlier sub-ranges only move my rows up
+    int below = 0;
     {
         int i = start + s0 + lane;
         const int iend = start + s1;
+        const uint32_t unv = (uint32_t)nv;
         for (; i + 96 < iend; i += 128) {
             const uint32_t k0 = pairs[i].x, k1 = pairs[i + 32].x, k2 = pairs[i + 64].x, k3 = pairs[i + 96].x;
-            atomicAdd(&mine[k0 - vbase], 1);
-            atomicAdd(&mine[k1 - vbase], 1);
-            atomicAdd(&mine[k2 - vbase], 1);
-            atomicAdd(&mine[k3 - vbase], 1);
+            if (k0 - vbase < unv) atomicAdd(&mine[k0 - vbase], 1);
+            if (k1 - vbase < unv) atomicAdd(&mine[k1 - vbase], 1);
+            if (k2 - vbase < unv) atomicAdd(&mine[k2 - vbase], 1);
+            if (k3 - vbase < unv) atomicAdd(&mine[k3 - vbase], 1);
+            below += (k0 < vbase) + (k1 < vbase) + (k2 < vbase) + (k3 < vbase);
         }
-        for (; i < iend; i += 32) atomicAdd(&mine[pairs[i].x - vbase], 1);
+        for (; i < iend; i += 32) {
+            const uint32_t k = pairs[i].x;
+            if (k - vbase < unv) atomicAdd(&mine[k - vbase], 1);
+            below += k < vbase;
+        }
+    }
+    if (vbits > 0) {  // block total of `below`
+        __shared__ int below_total;
+        if (tid == 0) below_total = 0;
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
+        if (lane == 0 && below) atomicAdd(&below_total, below);
+        __syncthreads();
+        below = below_total;
     }
     __syncthreads();
     // row starts: scan over the vertices of (sum over the warps); cursors: (vertex, warp) in that order
@@ -357,7 +379,7 @@ __global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
         if (lane < nwarps) warp_sums[lane] = winc - ws;
     }
     __syncthreads();
-    int run = start + warp_sums[warp] + inc - sum;
+    int run = start + below + warp_sums[warp] + inc - sum;
     for (int j = j0; j < j1; j++) {
         csr_start[vbase + j] = run;
         for (int w = 0; w < nwarps; w++) {
@@ -391,7 +413,8 @@ __global__ void __launch_bounds__(kBucketMaxThreads) bucket_csr_kernel(
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const bool valid = base + r * 32 + lane < iend;
+            const bool valid = base + r * 32 + lane < iend && eA[r].x - vbase < (uint32_t)nv;
+            if (vbits > 0 && !__any_sync(FULL, valid)) continue;  // a round without entries of my sub-range
             const int key = valid ? (int)(eA[r].x - vbase) : -1 - lane;
             const unsigned peers = __match_any_sync(FULL, key);
             const int rank = __popc(peers & ((1u << lane) - 1));
@@ -422,9 +445,11 @@ bool bucket_sort_to_csr(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_
                         std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile) {
     const int S = (int)seg_start.size() - 1;
     if (S <= 0 || E <= 0) return false;
-    int hi_bits = std::min(kSegMaxDigitBits, std::max(0, local_bits - 8));
+    static const int env_lo = [] { const char *e = getenv("DCRF_BUCKET_LO"); return e ? atoi(e) : 0; }();
+    const int want_lo = env_lo > 0 ? env_lo : 8;
+    int hi_bits = std::min(kSegMaxDigitBits, std::max(0, local_bits - want_lo));
     const int lo_bits = std::max(1, local_bits - hi_bits);
-    if (lo_bits > kBucketMaxLoBits || ((int64_t)S << hi_bits) > (int64_t)2000000000) return false;  // LSD passes instead
+    if (lo_bits > kBucketMaxLoBits || ((int64_t)S << (hi_bits + 3)) > (int64_t)2000000000) return false;  // LSD passes instead
     h_seg.assign(S + 1, 0);  // staging of asynchronous uploads: owned by the caller, outlives them
     h_tile.assign(S + 1, 0);
     for (int i = 0; i <= S; i++) h_seg[i] = (int32_t)seg_start[i];
@@ -451,13 +476,12 @@ bool bucket_sort_to_csr(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_
         }
     }
     ProfScope prof(DCRF_K_BUILD_CSR, prof_tag, s);
-    const int warps = std::min(kBucketMaxThreads / 32, kBucketSmemInts >> lo_bits);
-    const size_t smem = sizeof(int) * ((size_t)warps << lo_bits);
-    if (smem > 48 * 1024)  // per device: set whenever it is needed (a few hundred ns)
-        DCRF_CUDA(cudaFuncSetAttribute(bucket_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(int) * kBucketSmemInts)));
-    bucket_csr_kernel<<<(unsigned)((int64_t)S << hi_bits), warps * 32, smem, s>>>(
-        grouped, hist.p, si, hi_bits, lo_bits, bary, d1, (int32_t)E, (int32_t)M, csr_start, csr_pix, csr_w);
+    static const int env_warps = [] { const char *e = getenv("DCRF_BUCKET_WARPS"); return e ? atoi(e) : 0; }();
+    const int vbits = std::max(0, lo_bits - kBucketCtaBits);
+    const int warps = env_warps > 0 ? std::min(env_warps, kBucketMaxThreads / 32) : kBucketMaxThreads / 32;
+    const size_t smem = sizeof(int) * ((size_t)warps << (lo_bits - vbits));
+    bucket_csr_kernel<<<(unsigned)((int64_t)S << (hi_bits + vbits)), warps * 32, smem, s>>>(
+        grouped, hist.p, si, hi_bits, lo_bits, vbits, bary, d1, (int32_t)E, (int32_t)M, csr_start, csr_pix, csr_w);
     DCRF_LAUNCHED();
     return true;
 }
