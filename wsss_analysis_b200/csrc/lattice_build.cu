@@ -100,6 +100,28 @@ __device__ __forceinline__ uint32_t key_hash(const int4 k) {
     return h;
 }
 
+// Pixel record = first D coordinates of the remainder-0 point (int16 each) + the first D ranks (a nibble
+// each).  For D <= 6 both fit ONE int4 (coordinates in x, y, z, ranks in w): every look-up of the owner of
+// an occupied hash slot is a single 16-byte sector instead of a 16-byte and a 4-byte gather.  D = 7
+// keeps the ranks in a second array.
+struct PixRec {
+    int4 rem;       // w = 0 for D <= 6 (entry_key ignores coordinates >= D)
+    uint32_t rank;
+};
+template <int D>
+__device__ __forceinline__ PixRec load_rec(const int4 *__restrict__ rec_rem, const uint32_t *__restrict__ rec_rank,
+                                           int64_t p) {
+    PixRec r;
+    r.rem = rec_rem[p];
+    if (D <= 6) {
+        r.rank = (uint32_t)r.rem.w;
+        r.rem.w = 0;
+    } else {
+        r.rank = rec_rank[p];
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: one thread per pixel (Appendix A.2 + A.3 steps 2-6)
 // ---------------------------------------------------------------------------------------------
@@ -215,8 +237,46 @@ __global__ void __launch_bounds__(kThreads) lattice_point_kernel(
             rm[i] = 0;
         }
     }
-    rec_rem[gp] = pack_key(rm);
-    rec_rank[gp] = rp;
+    int4 rec = pack_key(rm);
+    if (D <= 6) rec.w = (int)rp;  // one-sector record (see load_rec)
+    else rec_rank[gp] = rp;
+    rec_rem[gp] = rec;
+}
+
+// The d+1 per-entry words of a pixel are contiguous (entry e = p * (d+1) + r): move them with the widest
+// aligned access instead of d+1 strided 4-byte ones (ncu: K3 / K4 sat at 80-86 % of the L1TEX pipe).
+template <int N>
+__device__ __forceinline__ void load_run(const int32_t *__restrict__ base, int32_t (&v)[N]) {
+    if (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            const int4 t = reinterpret_cast<const int4 *>(base)[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else if (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) {
+            const int2 t = reinterpret_cast<const int2 *>(base)[i];
+            v[2 * i] = t.x; v[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = base[i];
+    }
+}
+template <int N>
+__device__ __forceinline__ void store_run(int32_t *__restrict__ base, const int32_t (&v)[N]) {
+    if (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; i++)
+            reinterpret_cast<int4 *>(base)[i] = make_int4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if (N % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) reinterpret_cast<int2 *>(base)[i] = make_int2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) base[i] = v[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,8 +322,9 @@ __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
     const int b = find_image(g.pix_start, g.B, gp);
     int32_t *tab = table + tab_start[b];
     const uint32_t mask = (uint32_t)tab_mask[b];
-    const int4 rem = rec_rem[gp];
-    const uint32_t rp = rec_rank[gp];
+    const PixRec me = load_rec<D>(rec_rem, rec_rank, gp);
+    const int4 rem = me.rem;
+    const uint32_t rp = me.rank;
     const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rem, rp);
     if (!rl.leader) return;  // no warp-level operation below
 #pragma unroll 1
@@ -283,7 +344,8 @@ __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
             const int64_t cp = cur / (D + 1);
             const int cr = cur - (int32_t)cp * (D + 1);
             short ck[8];
-            entry_key<D>(rec_rem[cp], rec_rank[cp], cr, ck);
+            const PixRec owner = load_rec<D>(rec_rem, rec_rank, cp);
+            entry_key<D>(owner.rem, owner.rank, cr, ck);
             if (key_eq(pack_key(ck), pk)) {
                 if (e < cur) atomicMin(&tab[h], e);
                 break;
@@ -306,20 +368,20 @@ __global__ void __launch_bounds__(kThreads) first_mask_kernel(
     const bool valid = gp0 < Ntot;
     const int64_t gp = valid ? gp0 : Ntot - 1;
     const int b = find_image(g.pix_start, g.B, gp);
-    const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rec_rem[gp], rec_rank[gp]);
+    const PixRec me = load_rec<D>(rec_rem, rec_rank, gp);
+    const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], me.rem, me.rank);
     if (!valid) return;
     unsigned m = 0;
     if (rl.leader) {
         const int32_t *tab = table + tab_start[b];
-        int32_t rep[D + 1];
+        int32_t slot[D + 1], rep[D + 1];
+        load_run<D + 1>(slot_rep + gp * (D + 1), slot);
 #pragma unroll
-        for (int r = 0; r <= D; r++) rep[r] = tab[slot_rep[gp * (D + 1) + r]];
+        for (int r = 0; r <= D; r++) rep[r] = tab[slot[r]];
 #pragma unroll
-        for (int r = 0; r <= D; r++) {
-            const int32_t e = (int32_t)(gp * (D + 1) + r);
-            slot_rep[e] = rep[r];
-            if (rep[r] == e) m |= 1u << r;
-        }
+        for (int r = 0; r <= D; r++)
+            if (rep[r] == (int32_t)(gp * (D + 1) + r)) m |= 1u << r;
+        store_run<D + 1>(slot_rep + gp * (D + 1), rep);
     }
     cnt[gp] = __popc(m);
     mask8[gp] = (uint8_t)m;
@@ -338,13 +400,15 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
     const bool valid = gp0 < Ntot;
     const int64_t gp = valid ? gp0 : Ntot - 1;
     const int b = find_image(g.pix_start, g.B, gp);
-    const int4 rem = rec_rem[gp];
-    const uint32_t rp = rec_rank[gp];
+    const PixRec me = load_rec<D>(rec_rem, rec_rank, gp);
+    const int4 rem = me.rem;
+    const uint32_t rp = me.rank;
     const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rem, rp);
     const unsigned mine = rl.leader ? mask8[gp] : 0u;
     int32_t rep[D + 1];
 #pragma unroll
-    for (int r = 0; r <= D; r++) rep[r] = rl.leader ? slot_rep[gp * (D + 1) + r] : 0;
+    for (int r = 0; r <= D; r++) rep[r] = 0;
+    if (rl.leader) load_run<D + 1>(slot_rep + gp * (D + 1), rep);
     int32_t id[D + 1];
 #pragma unroll
     for (int r = 0; r <= D; r++) {
@@ -353,17 +417,26 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(
         id[r] = rl.leader ? pscan[pp] + __popc((unsigned)mask8[pp] & ((1u << rr) - 1u)) : 0;
     }
 #pragma unroll
+    for (int r = 0; r <= D; r++) id[r] = __shfl_sync(FULL, id[r], rl.src);
+    if (!valid) return;
+    const int64_t e0 = gp * (D + 1);
+    store_run<D + 1>(offset + e0, id);
+    // (vertex, entry) pairs for the CSR sort (K6): 16-byte stores of two pairs where d+1 is even
+    if ((D + 1) % 2 == 0) {
+        uint4 *sp = reinterpret_cast<uint4 *>(sort_pairs + e0);
+#pragma unroll
+        for (int r = 0; r + 1 <= D; r += 2)
+            sp[r / 2] = make_uint4((uint32_t)id[r], (uint32_t)(e0 + r), (uint32_t)id[r + 1], (uint32_t)(e0 + r + 1));
+    } else {
+#pragma unroll
+        for (int r = 0; r <= D; r++) sort_pairs[e0 + r] = make_uint2((uint32_t)id[r], (uint32_t)(e0 + r));
+    }
+#pragma unroll
     for (int r = 0; r <= D; r++) {
-        const int32_t v = __shfl_sync(FULL, id[r], rl.src);
-        if (valid) {
-            const int64_t e = gp * (D + 1) + r;
-            offset[e] = v;
-            sort_pairs[e] = make_uint2((uint32_t)v, (uint32_t)e);  // (vertex, entry) pairs for the CSR sort (K6)
-            if ((mine >> r) & 1u) {
-                short key[8];
-                entry_key<D>(rem, rp, r, key);
-                vkeys[v] = pack_key(key);
-            }
+        if ((mine >> r) & 1u) {
+            short key[8];
+            entry_key<D>(rem, rp, r, key);
+            vkeys[id[r]] = pack_key(key);
         }
     }
 }
@@ -518,7 +591,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     DevBuf<int4> rec_rem;
     DevBuf<uint32_t> rec_rank;
     rec_rem.alloc(Ntot, s);
-    rec_rank.alloc(Ntot, s);
+    if (D > 6) rec_rank.alloc(Ntot, s);
     out.bary.alloc(E, s);
     const int nbp = ceil_div(Ntot, kThreads);
     std::unique_ptr<ProfScope> prof(new ProfScope(DCRF_K_BUILD_POINT, D, s));
