@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
     const uint32_t rp = me.rank;
     const RunLeader rl = run_leader(valid, gp == (int64_t)g.pix_start[b], rem, rp);
     if (!rl.leader) return;  // no warp-level operation below
-#pragma unroll 1
+    int32_t slots[D + 1];
+#pragma unroll
     for (int r = 0; r <= D; r++) {
         short key[8];
         entry_key<D>(rem, rp, r, key);
@@ -352,8 +353,9 @@ __global__ void __launch_bounds__(kThreads) hash_insert_kernel(
             }
             h = (h + 1) & mask;
         }
-        slot_of[e] = (int32_t)h;  // leaders' entries only; the duplicates' slots are never read
+        slots[r] = (int32_t)h;
     }
+    store_run<D + 1>(slot_of + gp * (D + 1), slots);  // leaders' entries only; the duplicates' slots are never read
 }
 
 // K3: per pixel, which of its d+1 entries are the first occurrence of their key (bit r of mask8) and how

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_hist_kernel(const uint
     for (int i = threadIdx.x; i < radix; i += kSortThreads) hs[(int64_t)i * tiles + t] = h[i];
 }
 
-__global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
+__global__ void __launch_bounds__(kSortThreads, 4) seg_radix_scatter_kernel(
     const uint2 *__restrict__ pairs_in, uint2 *__restrict__ pairs_out, const int32_t *__restrict__ hist_scanned,
     SegInfo si, int shift, int digit_bits) {
     __shared__ int cnt[kSortWarps][kSegMaxRadix];
@@ -196,13 +196,17 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
     const int64_t end = si.seg_start[seg + 1];
     const uint32_t kb = (uint32_t)si.key_base[seg];
     const int64_t wbase = (int64_t)si.seg_start[seg] + (int64_t)t * kSortTile + (int64_t)warp * kSortWarpChunk;
-    uint2 k[kSortRounds];
+    // pass A keeps only the digits (one byte-pair each); the pairs are read again in pass B from L2 -- holding
+    // all 16 pairs in registers cost 102 registers per thread and a quarter of the SM's warp slots
+    uint32_t dig[kSortRounds / 2];
 #pragma unroll
     for (int r = 0; r < kSortRounds; r++) {
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < end;
-        k[r] = valid ? pairs_in[idx] : make_uint2(0u, 0u);
-        const int digit = valid ? (int)(((k[r].x - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        const uint32_t key = valid ? pairs_in[idx].x : 0u;
+        const int digit = valid ? (int)(((key - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        if (r & 1) dig[r / 2] |= (uint32_t)digit << 16;
+        else dig[r / 2] = (uint32_t)digit;
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[warp][digit] += __popc(peers);
         __syncwarp();
@@ -223,10 +227,11 @@ __global__ void __launch_bounds__(kSortThreads) seg_radix_scatter_kernel(
     for (int r = 0; r < kSortRounds; r++) {
         const int64_t idx = wbase + r * 32 + lane;
         const bool valid = idx < end;
-        const int digit = valid ? (int)(((k[r].x - kb) >> shift) & (radix - 1)) : (kSegMaxRadix + lane);
+        const uint2 kv = valid ? pairs_in[idx] : make_uint2(0u, 0u);
+        const int digit = (int)((dig[r / 2] >> ((r & 1) * 16)) & 0xffffu);  // (kSegMaxRadix + lane for invalid lanes)
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
         const int rank = __popc(peers & ((1u << lane) - 1));
-        if (valid) pairs_out[cnt[warp][digit] + rank] = k[r];  // one 8-byte scatter per pair
+        if (valid) pairs_out[cnt[warp][digit] + rank] = kv;  // one 8-byte scatter per pair
         __syncwarp();
         if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
         __syncwarp();
