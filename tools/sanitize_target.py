@@ -17,6 +17,7 @@ def batch(sizes, L, imgs=None, exact=False, arith=None, persistent=None):
 
 batch([(48, 36)] * 3, 21)                                   # uniform: replicated Gaussian lattice
 batch([(48, 36), (30, 50)], 6)                              # mixed sizes
+batch([(48, 36), (30, 50), (48, 36), (30, 50), (21, 17)], 6)  # repeated sizes: Gaussian lattice once per distinct size
 batch([(64, 64)], 21, [np.full((64, 64, 3), 90, np.uint8)]) # flat: long-row tail kernel
 batch([(40, 30)], 2); batch([(40, 30)], 1); batch([(20, 20)], 37); batch([(40, 30)], 5, exact=True)
 for L_ in (13, 16, 20, 24, 28, 32):                          # cooperative splat / slice at G = 4, 5, 6, 7, 8

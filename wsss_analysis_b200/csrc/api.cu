@@ -201,7 +201,28 @@ void stream_pool_release(cudaStream_t stream) {
     g_pools.erase(it);
 }
 
+// A lattice whose first build half has been enqueued (on `bs`) and whose second half still has to be:
+// everything the second half needs, kept alive until then.
+struct PendingBuild {
+    BuildState st;
+    FeatureSpec fs;
+    BatchGeom ug;                      // the distinct image sizes (position-only features, see add_pairwise)
+    DevBuf<int> ug_w, ug_h, ug_ps;
+    std::vector<int> ug_ps32, src;
+    bool shared = false;
+    Lattice single;
+    DevBuf<float> norm_single;
+    cudaStream_t bs = nullptr;         // the stream the build runs on
+    cudaEvent_t ev = nullptr;          // end of the first half on bs
+    int32_t *pinned = nullptr;         // page-locked [kPinnedInts] block for the vertex starts
+    DevBuf<uint8_t> rgb_stage;         // staged copies of caller host memory the first half reads
+    DevBuf<float> feat_stage;
+    ~PendingBuild();                   // an abandoned build: waits for its stream, returns the pinned block
+};
+
 struct Pairwise {
+    std::unique_ptr<PendingBuild> pending;
+    cudaStream_t built_on = nullptr;   // side stream that owns the lattice's memory (nullptr: the handle's stream)
     Lattice lat;
     DevBuf<float> norm;    // [Ntot]; empty for NO_NORMALIZATION
     DevBuf<float> compat;  // diagonal: [Lp]; matrix: [Lp*Lp] zero padded
@@ -407,8 +428,107 @@ void pack_tables(dcrf_handle *h, Lattice &lat, int ntype, const float *norm, cud
 }
 int wanted_tables(const dcrf_handle *h) { return h->arith == kArithFma ? kTablesFma : kTablesRef; }
 
+// ---- concurrent builds of small problems ----
+// One VOC image (or a batch of 41x41 SEC maps) builds each lattice in ~0.3 ms of ~30 dependent small
+// launches around one host synchronisation: latency, not throughput.  For such handles the FIRST half of
+// a build is only enqueued, on the side stream of its kernel, and add_pairwise returns; the second
+// halves run when the lattices are first needed (inference, export, ...).  The Gaussian and the bilateral
+// lattice of a model are then built side by side, and the host waits once per lattice for a vertex count
+// that is usually already there.  Larger problems fill the GPU with every kernel and keep the plain
+// single-stream build (and its single memory pool).
+constexpr int64_t kConcurrentBuildMaxPixels = 1000000;
+bool concurrent_builds_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("DCRF_CONCURRENT_BUILDS");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+constexpr int kPinnedInts = 4096;
+std::mutex g_pinned_mu;
+std::vector<int32_t *> g_pinned_free;  // page-locked blocks are expensive to create: recycled for the life of the process
+int32_t *pinned_get() {
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mu);
+        if (!g_pinned_free.empty()) {
+            int32_t *b = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return b;
+        }
+    }
+    int32_t *b = nullptr;
+    DCRF_CUDA(cudaMallocHost((void **)&b, sizeof(int32_t) * kPinnedInts));
+    return b;
+}
+void pinned_put(int32_t *b) {
+    if (!b) return;
+    std::lock_guard<std::mutex> lock(g_pinned_mu);
+    g_pinned_free.push_back(b);
+}
+}  // namespace
+namespace dcrf {
+PendingBuild::~PendingBuild() {
+    if (ev || pinned) {  // never finished (error path, handle destroyed before its first use)
+        if (bs) cudaStreamSynchronize(bs);  // its kernels read rgb_stage / write `pinned`
+        if (ev) cudaEventDestroy(ev);
+        pinned_put(pinned);
+    }
+}
+}  // namespace dcrf
+namespace {
+
+// second half of a build + norm + packed tables + replication + value buffers, on the build's stream
+void finish_pairwise(dcrf_handle *h, Pairwise &p) {
+    if (!p.pending) return;
+    PendingBuild &pb = *p.pending;
+    cudaStream_t s = pb.bs;
+    const int Lp = h->Lp;
+    const int64_t Ntot = h->geom.Ntot;
+    if (pb.ev) {
+        DCRF_CUDA(cudaEventSynchronize(pb.ev));
+    } else {
+        DCRF_CUDA(cudaStreamSynchronize(s));
+    }
+    const BatchGeom &bg = pb.shared ? pb.ug : h->geom;
+    Lattice &lat = pb.shared ? pb.single : p.lat;
+    DevBuf<float> &norm = pb.shared ? pb.norm_single : p.norm;
+    build_lattice_finish(bg, pb.fs, lat, pb.st, s);
+    // A.5: norm = filter(ones) through the value_size = 1 path
+    if (p.ntype != DCRF_NO_NORMALIZATION) {
+        ProfScope prof(DCRF_K_BUILD_NORM, lat.d, s);
+        norm.alloc(bg.Ntot, s);
+        launch_kernel_norm(lat, bg.Ntot, p.ntype, norm.p, s);
+    }
+    {
+        ProfScope prof(DCRF_K_BUILD_CSR, lat.d, s);
+        pack_tables(h, lat, p.ntype, norm.p, s);
+    }
+    if (pb.shared) {
+        if (norm.p) p.norm.alloc(Ntot, s);
+        launch_replicate_lattice(pb.single, pb.ug, norm.p, h->geom, pb.src, p.lat, p.norm.p, s);
+    }
+    p.valA.alloc((size_t)p.lat.M * Lp, s);
+    p.valB.alloc((size_t)p.lat.M * Lp, s);
+    if (s != h->stream) {  // the handle's stream continues after the build
+        if (!pb.ev) DCRF_CUDA(cudaEventCreateWithFlags(&pb.ev, cudaEventDisableTiming));
+        DCRF_CUDA(cudaEventRecord(pb.ev, s));
+        DCRF_CUDA(cudaStreamWaitEvent(h->stream, pb.ev, 0));
+        p.built_on = s;
+    }
+    if (pb.ev) cudaEventDestroy(pb.ev);  // released when the recorded work completes
+    pb.ev = nullptr;
+    pinned_put(pb.pinned);
+    pb.pinned = nullptr;
+    p.pending.reset();  // temporaries and staged inputs: freed in the order of the streams they were allocated on
+}
+
+void finish_builds(dcrf_handle *h) {
+    for (auto &p : h->pw) finish_pairwise(h, *p);
+}
+
 void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const float *compat, int ktype,
-                  int ntype) {
+                  int ntype, DevBuf<uint8_t> *rgb_stage = nullptr, DevBuf<float> *feat_stage = nullptr,
+                  bool caller_device_input = false) {
     DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
     DCRF_REQUIRE((int)h->pw.size() < kMaxPairwise, DCRF_EINVAL, "too many pairwise terms (max 4)");
     DCRF_REQUIRE(ktype >= DCRF_CONST_KERNEL && ktype <= DCRF_FULL_KERNEL, DCRF_EINVAL, "bad kernel type");
@@ -449,11 +569,11 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
     // for every image of a given size: it is built (and its norm filtered) ONCE per distinct size of
     // the batch and replicated with per-image id offsets (one size: bench.py's batches; a handful of
     // sizes: a batch of PASCAL VOC val images).
-    std::vector<int> src(h->geom.B, 0);
-    BatchGeom ug;   // the distinct sizes, in order of first appearance
-    DevBuf<int> ug_w, ug_h, ug_ps;
-    std::vector<int> ug_ps32;
-    bool shared = false;
+    p->pending.reset(new PendingBuild());
+    PendingBuild &pb = *p->pending;
+    pb.fs = fs;
+    pb.src.assign(h->geom.B, 0);
+    BatchGeom &ug = pb.ug;   // the distinct sizes, in order of first appearance
     if (fs.mode == 0 && h->geom.B > 1) {
         std::map<std::pair<int, int>, int> seen;
         for (int b = 0; b < h->geom.B; b++) {
@@ -464,53 +584,58 @@ void add_pairwise(dcrf_handle *h, const FeatureSpec &fs, int compat_kind, const 
                 ug.w.push_back(key.first);
                 ug.h.push_back(key.second);
             }
-            src[b] = it->second;
+            pb.src[b] = it->second;
         }
-        shared = (int)ug.w.size() < h->geom.B;
+        pb.shared = (int)ug.w.size() < h->geom.B;
     }
-    if (shared) {
+    // small problems: first half on the kernel's side stream, second half when the lattice is needed
+    const int k = (int)h->pw.size();
+    const bool concurrent = Ntot <= kConcurrentBuildMaxPixels && !h->prof.on && k < kMaxPairwise - 1 &&
+                            h->geom.B + 1 <= kPinnedInts && concurrent_builds_enabled();
+    cudaStream_t bs = concurrent ? h->streams->get_side(k) : s;
+    pb.bs = bs;
+    if (concurrent) {
+        // everything enqueued on the handle's stream so far (geometry uploads, staged inputs) comes first
+        DCRF_CUDA(cudaEventCreateWithFlags(&pb.ev, cudaEventDisableTiming));
+        DCRF_CUDA(cudaEventRecord(pb.ev, s));
+        DCRF_CUDA(cudaStreamWaitEvent(bs, pb.ev, 0));
+        pb.pinned = pinned_get();
+        if (rgb_stage) pb.rgb_stage = std::move(*rgb_stage);
+        if (feat_stage) pb.feat_stage = std::move(*feat_stage);
+    }
+    if (pb.shared) {
         ug.B = (int)ug.w.size();
         ug.pix_start.assign(ug.B + 1, 0);
-        ug_ps32.assign(ug.B + 1, 0);
+        pb.ug_ps32.assign(ug.B + 1, 0);
         for (int u = 0; u < ug.B; u++) {
             ug.pix_start[u + 1] = ug.pix_start[u] + (int64_t)ug.w[u] * ug.h[u];
-            ug_ps32[u + 1] = (int)ug.pix_start[u + 1];
+            pb.ug_ps32[u + 1] = (int)ug.pix_start[u + 1];
         }
         ug.Ntot = ug.pix_start[ug.B];
-        ug_w.alloc(ug.B, s);
-        ug_h.alloc(ug.B, s);
-        ug_ps.alloc(ug.B + 1, s);
-        DCRF_CUDA(copy_h2d(ug_w.p, ug.w.data(), sizeof(int) * ug.B, s));
-        DCRF_CUDA(copy_h2d(ug_h.p, ug.h.data(), sizeof(int) * ug.B, s));
-        DCRF_CUDA(copy_h2d(ug_ps.p, ug_ps32.data(), sizeof(int) * (ug.B + 1), s));
-        ug.d_w = ug_w.p;
-        ug.d_h = ug_h.p;
-        ug.d_pix_start = ug_ps.p;
+        pb.ug_w.alloc(ug.B, bs);
+        pb.ug_h.alloc(ug.B, bs);
+        pb.ug_ps.alloc(ug.B + 1, bs);
+        DCRF_CUDA(copy_h2d(pb.ug_w.p, ug.w.data(), sizeof(int) * ug.B, bs));
+        DCRF_CUDA(copy_h2d(pb.ug_h.p, ug.h.data(), sizeof(int) * ug.B, bs));
+        DCRF_CUDA(copy_h2d(pb.ug_ps.p, pb.ug_ps32.data(), sizeof(int) * (ug.B + 1), bs));
+        ug.d_w = pb.ug_w.p;
+        ug.d_h = pb.ug_h.p;
+        ug.d_pix_start = pb.ug_ps.p;
     }
-    const BatchGeom &bg = shared ? ug : h->geom;
-    Lattice single;
-    Lattice &lat = shared ? single : p->lat;
-    DevBuf<float> norm_single;
-    DevBuf<float> &norm = shared ? norm_single : p->norm;
-    build_lattice(bg, fs, lat, s);
-    // A.5: norm = filter(ones) through the value_size = 1 path
-    if (ntype != DCRF_NO_NORMALIZATION) {
-        ProfScope prof(DCRF_K_BUILD_NORM, lat.d, s);
-        norm.alloc(bg.Ntot, s);
-        launch_kernel_norm(lat, bg.Ntot, ntype, norm.p, s);
+    const BatchGeom &bg = pb.shared ? ug : h->geom;
+    Lattice &lat = pb.shared ? pb.single : p->lat;
+    build_lattice_begin(bg, fs, lat, pb.st, pb.pinned, bs);
+    if (concurrent) {
+        DCRF_CUDA(cudaEventRecord(pb.ev, bs));
+        // memory of the CALLER on the device (a torch tensor) is only read by the first kernels: it must
+        // not be released to its allocator before they ran
+        if (caller_device_input) DCRF_CUDA(cudaEventSynchronize(pb.ev));
+        h->pw.push_back(std::move(p));
+        return;
     }
-    {
-        ProfScope prof(DCRF_K_BUILD_CSR, lat.d, s);
-        pack_tables(h, lat, ntype, norm.p, s);
-    }
-    if (shared) {
-        if (norm.p) p->norm.alloc(Ntot, s);
-        // (the uploads of ug's arrays completed before build_lattice's host synchronisation returned)
-        launch_replicate_lattice(single, ug, norm.p, h->geom, src, p->lat, p->norm.p, s);
-    }
-    p->valA.alloc((size_t)p->lat.M * Lp, s);
-    p->valB.alloc((size_t)p->lat.M * Lp, s);
+    Pairwise &pr = *p;
     h->pw.push_back(std::move(p));
+    finish_pairwise(h, pr);
 }
 
 
@@ -543,6 +668,7 @@ void start_inference(dcrf_handle *h) {
 
 void step_inference(dcrf_handle *h) {
     DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "stepInference before startInference");
+    finish_builds(h);
     const bool seq = h->L <= 2;
     // packed-table kernels index rows with 32 bits: (largest row index) * (float4 per row) < 2^32
     int64_t max_rows = h->geom.Ntot;
@@ -660,6 +786,7 @@ void run_inference(dcrf_handle *h, int n_iter) {
     DCRF_REQUIRE(n_iter >= 0, DCRF_EINVAL, "n_iter must be >= 0");
     DCRF_REQUIRE(h->L >= 1, DCRF_ESTATE, "model has no labels");
     join_upload(h);
+    finish_builds(h);
     if (try_persistent(h, n_iter)) {
         h->q_valid = true;
         return;
@@ -673,6 +800,7 @@ void run_inference(dcrf_handle *h, int n_iter) {
 
 Pairwise &get_pw(dcrf_handle *h, int k) {
     DCRF_REQUIRE(k >= 0 && k < (int)h->pw.size(), DCRF_EINVAL, "pairwise index out of range");
+    finish_pairwise(h, *h->pw[k]);
     return *h->pw[k];
 }
 
@@ -716,6 +844,20 @@ void dcrf_destroy(dcrf_t *h) {
         if (h->ev_upload_begin) {
             cudaEventDestroy(h->ev_upload_begin);
             cudaEventDestroy(h->ev_upload_end);
+        }
+        // lattices built on a side stream free their memory in THAT stream's order: it must come after
+        // everything the handle's stream still does with them
+        {
+            cudaEvent_t ev = nullptr;
+            for (auto &p : h->pw) {
+                if (!p->built_on) continue;
+                if (!ev) {
+                    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) break;
+                    cudaEventRecord(ev, h->stream);
+                }
+                cudaStreamWaitEvent(p->built_on, ev, 0);
+            }
+            if (ev) cudaEventDestroy(ev);
         }
         h->pw.clear();
         h->unary.release();
@@ -988,7 +1130,7 @@ int dcrf_add_pairwise_bilateral(dcrf_t *h, float sx, float sy, float sr, float s
         fs.d = 5;
         fs.s[0] = sx; fs.s[1] = sy; fs.s[2] = sr; fs.s[3] = sg; fs.s[4] = sb;
         fs.rgb = to_device(h, rgb, (size_t)h->geom.Ntot * 3, on_device, stage);
-        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
+        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type, &stage, nullptr, on_device != 0);
         if (!on_device) host_sync(h);
     });
 }
@@ -1007,7 +1149,7 @@ int dcrf_add_pairwise_energy(dcrf_t *h, const float *features, int d, int on_dev
         fs.mode = 2;
         fs.d = d;
         fs.features = to_device(h, features, (size_t)h->geom.Ntot * d, on_device, stage);
-        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type);
+        add_pairwise(h, fs, compat_kind, compat, kernel_type, normalization_type, nullptr, &stage, on_device != 0);
         if (!on_device) host_sync(h);
     });
 }
@@ -1137,6 +1279,7 @@ int dcrf_kl_divergence(dcrf_t *h, double *kl_out) {
         DCRF_REQUIRE(h->q_valid, DCRF_ESTATE, "no running Q: call startInference first");
         DeviceGuard guard(h->device);
         join_upload(h);
+        finish_builds(h);
         cudaStream_t s = h->stream;
         const int64_t Ntot = h->geom.Ntot;
         const bool seq = h->L <= 2;

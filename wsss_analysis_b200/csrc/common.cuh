@@ -187,6 +187,24 @@ struct Lattice {
     DevBuf<int> n_long;            // [1] their number (device side)
 };
 
+// A build has two halves around its one host synchronisation (the vertex count sizes the arrays of the
+// second half).  build_lattice() runs both on one stream; small problems run the first halves of all
+// their kernels' lattices concurrently on separate streams (api.cu) -- the temporaries live here.
+struct BuildState {
+    DevBuf<int4> rec_rem;
+    DevBuf<uint32_t> rec_rank;
+    DevBuf<int32_t> slot_of, pscan, d_vert_start;
+    DevBuf<uint8_t> mask8;
+    std::vector<int32_t> h_vs_own;  // destination of the vertex starts when the caller gives no pinned block
+    int32_t *h_vs = nullptr;        // [B+1] vertex starts: valid once the stream reached the end of begin()
+};
+// first half: point, hash, first-occurrence masks, scan, D2H of the per-image vertex starts into
+// `pinned_vs` (page-locked, asynchronous) or into st.h_vs_own (pageable: the copy itself blocks)
+void build_lattice_begin(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st, int32_t *pinned_vs,
+                         cudaStream_t stream);
+// second half, once the stream has reached the end of the first: ids, neighbours, CSR rows
+void build_lattice_finish(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st,
+                          cudaStream_t stream);
 void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t stream);
 // `one`: lattice (packed tables included) over the DISTINCT image sizes `og` of the batch `g`; image b of
 // the batch is unique image src[b].  `out`: the same lattice for every image of the batch laid back to

@@ -574,7 +574,8 @@ __global__ void __launch_bounds__(kThreads) csr_finalize_kernel(
 
 
 template <int D>
-void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {
+void build_begin_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st, int32_t *pinned_vs,
+                      cudaStream_t s) {
     const int B = g.B;
     const int64_t Ntot = g.Ntot;
     const int d1 = D + 1;
@@ -590,8 +591,8 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     for (int i = 0; i < D; i++)
         scale.s[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * (double)inv_std_dev);
 
-    DevBuf<int4> rec_rem;
-    DevBuf<uint32_t> rec_rank;
+    DevBuf<int4> &rec_rem = st.rec_rem;
+    DevBuf<uint32_t> &rec_rank = st.rec_rank;
     rec_rem.alloc(Ntot, s);
     if (D > 6) rec_rank.alloc(Ntot, s);
     out.bary.alloc(E, s);
@@ -627,7 +628,7 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
     table.alloc(tab_start[B], s);
     DCRF_CUDA(cudaMemsetAsync(table.p, 0xFF, sizeof(int32_t) * tab_start[B], s));
 
-    DevBuf<int32_t> slot_of;
+    DevBuf<int32_t> &slot_of = st.slot_of;
     slot_of.alloc(E, s);
     hash_insert_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, d_tab_start.p, d_tab_mask.p, rec_rem.p,
                                                   rec_rank.p, table.p, slot_of.p);
@@ -635,27 +636,48 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
 
     prof.reset();
     prof.reset(new ProfScope(DCRF_K_BUILD_NUMBER, D, s));
-    DevBuf<int32_t> pscan;   // per pixel: count of first occurrences, scanned in place
-    DevBuf<uint8_t> mask8;   // per pixel: which remainders are first occurrences
+    DevBuf<int32_t> &pscan = st.pscan;   // per pixel: count of first occurrences, scanned in place
+    DevBuf<uint8_t> &mask8 = st.mask8;   // per pixel: which remainders are first occurrences
     pscan.alloc(Ntot + 1, s);
     mask8.alloc(Ntot, s);
-    const int nbe = ceil_div(E, kThreads);
     first_mask_kernel<D><<<nbp, kThreads, 0, s>>>(gd, Ntot, d_tab_start.p, table.p, rec_rem.p, rec_rank.p,
                                                  slot_of.p, pscan.p, mask8.p);
     DCRF_LAUNCHED();
     exclusive_scan_i32(pscan.p, pscan.p, Ntot, s);
 
     // vertex counts: total + per image (host needs them to size everything else)
-    DevBuf<int32_t> d_vert_start;
+    DevBuf<int32_t> &d_vert_start = st.d_vert_start;
     d_vert_start.alloc(B + 1, s);
     vert_start_kernel<<<ceil_div(B + 1, 128), 128, 0, s>>>(g.d_pix_start, B, pscan.p, d_vert_start.p);
     DCRF_LAUNCHED();
-    std::vector<int32_t> h_vs(B + 1);
-    DCRF_CUDA(copy_d2h(h_vs.data(), d_vert_start.p, sizeof(int32_t) * (B + 1), s));
-    DCRF_CUDA(cudaStreamSynchronize(s));
-    out.vert_start.assign(h_vs.begin(), h_vs.end());
+    if (pinned_vs) {
+        st.h_vs = pinned_vs;
+    } else {
+        st.h_vs_own.assign(B + 1, 0);
+        st.h_vs = st.h_vs_own.data();
+    }
+    DCRF_CUDA(copy_d2h(st.h_vs, d_vert_start.p, sizeof(int32_t) * (B + 1), s));
+}
+
+template <int D>
+void build_finish_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st, cudaStream_t s) {
+    (void)f;
+    const int B = g.B;
+    const int64_t Ntot = g.Ntot;
+    const int d1 = D + 1;
+    const int64_t E = Ntot * d1;
+    GeomDev gd{g.d_w, g.d_h, g.d_pix_start, B};
+    const int nbp = ceil_div(Ntot, kThreads);
+    const int nbe = ceil_div(E, kThreads);
+    DevBuf<int4> &rec_rem = st.rec_rem;
+    DevBuf<uint32_t> &rec_rank = st.rec_rank;
+    DevBuf<int32_t> &slot_of = st.slot_of, &pscan = st.pscan, &d_vert_start = st.d_vert_start;
+    DevBuf<uint8_t> &mask8 = st.mask8;
+    const int32_t *h_vs = st.h_vs;
+    out.vert_start.assign(h_vs, h_vs + B + 1);
     const int64_t M = h_vs[B];
     out.M = M;
+    std::unique_ptr<ProfScope> prof(new ProfScope(DCRF_K_BUILD_NUMBER, D, s));
 
     out.offset.alloc(E, s);
     out.vkeys.alloc((size_t)M * 8, s);
@@ -741,18 +763,33 @@ void build_impl(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStre
 
 }  // namespace
 
-void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {
-    switch (f.d) {
-        case 1: build_impl<1>(g, f, out, s); break;
-        case 2: build_impl<2>(g, f, out, s); break;
-        case 3: build_impl<3>(g, f, out, s); break;
-        case 4: build_impl<4>(g, f, out, s); break;
-        case 5: build_impl<5>(g, f, out, s); break;
-        case 6: build_impl<6>(g, f, out, s); break;
-        case 7: build_impl<7>(g, f, out, s); break;
-        default:
-            throw Error{DCRF_EINVAL, "feature dimension d must be in [1, 7]"};
+#define DCRF_DISPATCH_D(d, ...)                                                  \
+    switch (d) {                                                                 \
+        case 1: { constexpr int D = 1; __VA_ARGS__; } break;                     \
+        case 2: { constexpr int D = 2; __VA_ARGS__; } break;                     \
+        case 3: { constexpr int D = 3; __VA_ARGS__; } break;                     \
+        case 4: { constexpr int D = 4; __VA_ARGS__; } break;                     \
+        case 5: { constexpr int D = 5; __VA_ARGS__; } break;                     \
+        case 6: { constexpr int D = 6; __VA_ARGS__; } break;                     \
+        case 7: { constexpr int D = 7; __VA_ARGS__; } break;                     \
+        default:                                                                 \
+            throw Error{DCRF_EINVAL, "feature dimension d must be in [1, 7]"};   \
     }
+
+void build_lattice_begin(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st, int32_t *pinned_vs,
+                         cudaStream_t s) {
+    DCRF_DISPATCH_D(f.d, build_begin_impl<D>(g, f, out, st, pinned_vs, s));
+}
+
+void build_lattice_finish(const BatchGeom &g, const FeatureSpec &f, Lattice &out, BuildState &st, cudaStream_t s) {
+    DCRF_DISPATCH_D(f.d, build_finish_impl<D>(g, f, out, st, s));
+}
+
+void build_lattice(const BatchGeom &g, const FeatureSpec &f, Lattice &out, cudaStream_t s) {
+    BuildState st;
+    build_lattice_begin(g, f, out, st, nullptr, s);
+    DCRF_CUDA(cudaStreamSynchronize(s));
+    build_lattice_finish(g, f, out, st, s);
 }
 
 
