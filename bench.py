@@ -273,12 +273,12 @@ def hbm_peak():
 
 
 def csrc_digest():
-    """SHA-256 over the CUDA sources: profiles/r2_traffic.json is only quoted for the build it was captured on."""
+    """SHA-256 over the CUDA sources that define the captured (per-iteration) kernels and their data
+    layout: profiles/r2_traffic.json is only quoted while the kernels it was captured on are unchanged."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "wsss_analysis_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(d, f), "rb").read())
+    for f in ("common.cuh", "filter.cu", "softmax_ref.cuh"):
+        h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 

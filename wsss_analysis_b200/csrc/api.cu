@@ -108,8 +108,12 @@ std::shared_ptr<StreamSet> thread_set(int dev) {
 
 // sets of caller-provided primaries (torch streams, dcrf_stream_create): kept in a registry so that
 // handle after handle on the same stream reuses the same side / upload streams
-std::mutex g_sets_mu;
-std::map<std::pair<int, cudaStream_t>, std::shared_ptr<StreamSet>> g_sets;
+// (The registries of this file are never destroyed: static destructors run in reverse order of definition
+// at process exit, and a StreamSet dying there would release its pools into a map that is already gone
+// -- glibc "double free or corruption" once side streams own pools.  The process is ending; the driver
+// reclaims streams and pools.)
+std::mutex &g_sets_mu = *new std::mutex();
+auto &g_sets = *new std::map<std::pair<int, cudaStream_t>, std::shared_ptr<StreamSet>>();
 std::shared_ptr<StreamSet> caller_set(int dev, cudaStream_t primary) {
     std::lock_guard<std::mutex> lock(g_sets_mu);
     auto &slot = g_sets[std::make_pair(dev, primary)];
@@ -135,8 +139,8 @@ void trace_slow(const char *what, double t0, size_t bytes) {
     if (dt > 2.0) fprintf(stderr, "[dcrf trace] %s blocked %.1f ms (%zu bytes)\n", what, dt, bytes);
 }
 
-static std::mutex g_pool_mu;
-static std::map<std::pair<int, cudaStream_t>, cudaMemPool_t> g_pools;  // key: (device, stream)
+static std::mutex &g_pool_mu = *new std::mutex();
+static auto &g_pools = *new std::map<std::pair<int, cudaStream_t>, cudaMemPool_t>();  // key: (device, stream); never destroyed
 
 cudaMemPool_t stream_pool(cudaStream_t stream) {
     int dev = 0;
@@ -445,8 +449,8 @@ bool concurrent_builds_enabled() {
     return on;
 }
 constexpr int kPinnedInts = 4096;
-std::mutex g_pinned_mu;
-std::vector<int32_t *> g_pinned_free;  // page-locked blocks are expensive to create: recycled for the life of the process
+std::mutex &g_pinned_mu = *new std::mutex();
+auto &g_pinned_free = *new std::vector<int32_t *>();  // page-locked blocks are expensive to create: recycled for the life of the process
 int32_t *pinned_get() {
     {
         std::lock_guard<std::mutex> lock(g_pinned_mu);
