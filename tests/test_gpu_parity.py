@@ -386,3 +386,33 @@ def test_c_abi_error_codes_and_messages(mods):
     lib.dcrf_destroy(h)
     lib.dcrf_destroy(None)  # no-op
     assert lib.dcrf_launch_count() > 0
+
+
+def test_lsd_sort_path_gives_the_same_rows():
+    """The CSR rows normally come from one radix pass + the bucket kernel; images with more than 2^23
+    lattice vertices fall back to the multi-pass LSD sort + finalising kernel.  DCRF_SORT_LSD=1 forces that
+    path (read once per process, hence the subprocesses): marginals of a mixed batch must be bit-identical."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import hashlib, numpy as np\n"
+        "from wsss_analysis_b200 import densecrf as G, synthetic as S\n"
+        "sizes = [(70, 50), (33, 61), (70, 50)]\n"
+        "imgs = [S.natural_image(h, w, 7 + i) for i, (w, h) in enumerate(sizes)]\n"
+        "imgs[1][:] = 120\n"   # a flat image: very long rows
+        "Us = [S.random_unary(6, w * h, 7 + i) for i, (w, h) in enumerate(sizes)]\n"
+        "d = G.DenseCRFBatch(sizes, 6); d.set_arithmetic('reference'); d.setUnaryEnergy(Us)\n"
+        "d.addPairwiseGaussian(sxy=3, compat=3); d.addPairwiseBilateral(sxy=30, srgb=13, rgbim=imgs, compat=10)\n"
+        "Q = d.inference(4)\n"
+        "print(hashlib.sha256(b''.join(np.ascontiguousarray(q).tobytes() for q in Q)).hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for lsd in ("0", "1"):
+        env = dict(os.environ, DCRF_SORT_LSD=lsd, PYTHONPATH=root)
+        out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append(out.stdout.strip().splitlines()[-1])
+    assert len(digests[0]) == 64 and digests[0] == digests[1]

@@ -450,6 +450,10 @@ bool bucket_sort_to_csr(uint2 *pairs_a, uint2 *pairs_b, const std::vector<int64_
                         std::vector<int32_t> &h_seg, std::vector<int32_t> &h_tile) {
     const int S = (int)seg_start.size() - 1;
     if (S <= 0 || E <= 0) return false;
+    // DCRF_SORT_LSD=1: take the multi-pass LSD path that otherwise only images with more than 2^23 vertices
+    // reach (kept under test by tests/test_gpu_parity.py::test_lsd_sort_path_gives_the_same_rows)
+    static const bool force_lsd = [] { const char *e = getenv("DCRF_SORT_LSD"); return e && atoi(e) != 0; }();
+    if (force_lsd) return false;
     static const int env_lo = [] { const char *e = getenv("DCRF_BUCKET_LO"); return e ? atoi(e) : 0; }();
     const int want_lo = env_lo > 0 ? env_lo : 8;
     int hi_bits = std::min(kSegMaxDigitBits, std::max(0, local_bits - want_lo));
